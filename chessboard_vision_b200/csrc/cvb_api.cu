@@ -1,0 +1,675 @@
+// C ABI of libcvb200.so (see include/cvb200.h).  Handle, workspace, argument
+// checking and the composition of the kernel launchers into the reference's
+// methods (frame_enhancer.py:101-181, board_detection.py:61-71,
+// change_detector.py:36-167, piece_detector.py:70-97).
+#include "cvb_internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+static thread_local char g_err[512] = "";
+
+void cvb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cvb_ws(cvb_handle *h, DevBuf &b, size_t bytes, void **out)
+{
+    if (bytes > b.cap) {
+        // a grow may free a buffer that queued work still reads
+        CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+        if (b.p) CVB_CHECK_CUDA(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+        size_t cap = bytes + bytes / 8 + 256;
+        CVB_CHECK_CUDA(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return CVB_OK;
+}
+
+#define WS(buf, type, count, var) \
+    type *var = nullptr;          \
+    CVB_TRY(cvb_ws(h, h->buf, sizeof(type) * (size_t)(count), (void **)&var))
+
+#define REQ_H(h) CVB_REQUIRE((h) != nullptr, "null handle")
+#define REQ_IMG(n, H, W)                                                                                      \
+    CVB_REQUIRE((n) >= 1 && (n) <= 65535 && (H) >= 1 && (W) >= 1 && (H) <= 32768 && (W) <= 32768,              \
+                "bad batch/shape n=%d H=%d W=%d", (n), (H), (W))
+
+static void drop_rect_cache(cvb_handle *h);
+
+extern "C" {
+
+int cvb_version(void) { return CVB_VERSION; }
+const char *cvb_last_error(void) { return g_err; }
+
+int cvb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cvb_create(int device, cvb_handle **out)
+{
+    CVB_REQUIRE(out != nullptr, "null out pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        cvb_set_error("no CUDA device available (%s); libcvb200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return CVB_ERR_NO_DEVICE;
+    }
+    CVB_REQUIRE(device >= 0 && device < n, "device %d out of range (0..%d)", device, n - 1);
+    CVB_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CVB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        cvb_set_error("device %d is sm_%d%d; libcvb200 is built for sm_100a only", device, prop.major, prop.minor);
+        return CVB_ERR_NO_DEVICE;
+    }
+    cvb_handle *h = new cvb_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    CVB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CVB_CHECK_CUDA(cudaMalloc(&h->d_tables, sizeof(CvbTables)));
+    CVB_CHECK_CUDA(cudaMemcpy(h->d_tables, &cvb_host_tables(), sizeof(CvbTables), cudaMemcpyHostToDevice));
+    *out = h;
+    return CVB_OK;
+}
+
+void cvb_destroy(cvb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
+                      &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
+                      &h->ws_stats, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_color) cudaFree(h->d_color);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    drop_rect_cache(h);
+    delete h;
+}
+
+int cvb_set_stream(cvb_handle *h, void *cuda_stream)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return CVB_OK;
+}
+int cvb_synchronize(cvb_handle *h)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+int64_t cvb_launch_count(cvb_handle *h) { return h ? h->launches : -1; }
+
+int cvb_malloc(cvb_handle *h, size_t bytes, void **dptr)
+{
+    REQ_H(h);
+    CVB_REQUIRE(dptr != nullptr, "null out pointer");
+    CVB_CHECK_CUDA(cudaSetDevice(h->device));
+    CVB_CHECK_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return CVB_OK;
+}
+int cvb_free(cvb_handle *h, void *dptr)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    CVB_CHECK_CUDA(cudaFree(dptr));
+    return CVB_OK;
+}
+int cvb_host_alloc(size_t bytes, void **hptr)
+{
+    CVB_REQUIRE(hptr != nullptr, "null out pointer");
+    CVB_CHECK_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return CVB_OK;
+}
+int cvb_host_free(void *hptr)
+{
+    CVB_CHECK_CUDA(cudaFreeHost(hptr));
+    return CVB_OK;
+}
+int cvb_memcpy_h2d(cvb_handle *h, void *dst, const void *src, size_t bytes)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return CVB_OK;
+}
+int cvb_memcpy_d2h(cvb_handle *h, void *dst, const void *src, size_t bytes)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return CVB_OK;
+}
+int cvb_memset(cvb_handle *h, void *dst, int value, size_t bytes)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaMemsetAsync(dst, value, bytes, h->stream));
+    return CVB_OK;
+}
+int cvb_event_create(void **ev)
+{
+    CVB_REQUIRE(ev != nullptr, "null out pointer");
+    cudaEvent_t e;
+    CVB_CHECK_CUDA(cudaEventCreate(&e));
+    *ev = e;
+    return CVB_OK;
+}
+int cvb_event_destroy(void *ev)
+{
+    CVB_CHECK_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return CVB_OK;
+}
+int cvb_event_record(cvb_handle *h, void *ev)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)ev, h->stream));
+    return CVB_OK;
+}
+int cvb_event_elapsed_ms(void *start, void *stop, float *ms)
+{
+    CVB_CHECK_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    CVB_CHECK_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return CVB_OK;
+}
+
+void cvb_enhance_params_default(cvb_enhance_params *p)
+{
+    p->clahe_clip_limit = 3.0; p->tiles_x = 8; p->tiles_y = 8;
+    p->bilateral_d = 9; p->sigma_color = 75.0; p->sigma_space = 75.0;
+}
+void cvb_square_params_default(cvb_square_params *p)
+{
+    p->ops = CVB_SQ_PD_STATS; p->pd_blur = 5; p->cd_blur = 5;
+    p->z_threshold = 2.5f; p->alpha = 0.1f; p->one_minus_alpha = (float)(1 - 0.1);
+    p->initial_variance = 100.0f; p->min_variance = 10.0f;
+}
+void cvb_pipeline_params_default(cvb_pipeline_params *p)
+{
+    cvb_enhance_params_default(&p->enhance);
+    cvb_square_params_default(&p->squares);
+    p->warp_enhanced = 1; p->board_size = 620;
+}
+
+int cvb_get_tables(uint16_t *gamma256, uint16_t *cbrt2048, int32_t *lab2yf512, uint8_t *invgamma4096, uint8_t *ltab2048)
+{
+    const CvbTables &t = cvb_host_tables();
+    if (gamma256) memcpy(gamma256, t.gamma, sizeof t.gamma);
+    if (cbrt2048) memcpy(cbrt2048, t.cbrt, sizeof t.cbrt);
+    if (lab2yf512) memcpy(lab2yf512, t.lab2yf, sizeof t.lab2yf);
+    if (invgamma4096) memcpy(invgamma4096, t.invgamma, sizeof t.invgamma);
+    if (ltab2048) memcpy(ltab2048, t.ltab, sizeof t.ltab);
+    return CVB_OK;
+}
+int cvb_get_bilateral_tables(double sigma_color, double sigma_space, float *color768, float *space81)
+{
+    cvb_host_bilateral_tables(sigma_color, sigma_space, color768, space81);
+    return CVB_OK;
+}
+int cvb_gaussian_kernel_q8(int ksize, int *q)
+{
+    CVB_REQUIRE(q != nullptr, "null out pointer");
+    int rc = cvb_host_gaussian_q8(ksize, q);
+    if (rc != CVB_OK) cvb_set_error("GaussianBlur ksize %d unsupported (odd, 1..31)", ksize);
+    return rc;
+}
+int cvb_get_perspective_transform(const float *src_xy4, const float *dst_xy4, double *M9)
+{
+    CVB_REQUIRE(src_xy4 && dst_xy4 && M9, "null pointer");
+    int rc = cvb_host_get_perspective(src_xy4, dst_xy4, M9);
+    if (rc != CVB_OK) cvb_set_error("degenerate quadrilateral (singular system)");
+    return rc;
+}
+
+// ---- stage-isolated entry points ----------------------------------------------------------
+int cvb_bgr2lab_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *lab)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && lab, "null image pointer");
+    return launch_bgr2lab(h, bgr, (long)n * H * W, lab);
+}
+int cvb_lab2bgr_dev(cvb_handle *h, const uint8_t *lab, int n, int H, int W, uint8_t *bgr)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && lab, "null image pointer");
+    return launch_lab2bgr(h, lab, (long)n * H * W, bgr);
+}
+
+static int clahe_tables(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W, const ClaheGeom &g,
+                        int32_t **hist_io, uint8_t **lut_io, int32_t *minmax_init)
+{
+    const size_t nt = (size_t)g.tiles_x * g.tiles_y * n;
+    int32_t *hist = *hist_io;
+    uint8_t *lut = *lut_io;
+    if (!hist) CVB_TRY(cvb_ws(h, h->ws_hist, nt * 256 * sizeof(int32_t), (void **)&hist));
+    if (!lut) CVB_TRY(cvb_ws(h, h->ws_lut, nt * 256, (void **)&lut));
+    CVB_TRY(launch_tile_hist(h, src, from_bgr, n, H, W, g, hist, minmax_init));
+    CVB_TRY(launch_clahe_lut(h, hist, n, g, lut));
+    *hist_io = hist; *lut_io = lut;
+    return CVB_OK;
+}
+
+int cvb_clahe_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, double clip_limit, int tiles_x, int tiles_y,
+                  uint8_t *out, int32_t *hist_out, uint8_t *lut_out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(plane && out, "null image pointer");
+    ClaheGeom g;
+    CVB_TRY(cvb_clahe_geom(H, W, clip_limit, tiles_x, tiles_y, &g));
+    CVB_TRY(clahe_tables(h, plane, 0, n, H, W, g, &hist_out, &lut_out, nullptr));
+    return launch_clahe_apply_plane(h, plane, n, H, W, g, lut_out, out);
+}
+int cvb_correct_lighting_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, double clip_limit, int tiles_x,
+                             int tiles_y, uint8_t *out, int32_t *hist_out, uint8_t *lut_out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && out, "null image pointer");
+    ClaheGeom g;
+    CVB_TRY(cvb_clahe_geom(H, W, clip_limit, tiles_x, tiles_y, &g));
+    CVB_TRY(clahe_tables(h, bgr, 1, n, H, W, g, &hist_out, &lut_out, nullptr));
+    return launch_correct_lighting(h, bgr, n, H, W, g, lut_out, out);
+}
+int cvb_bilateral_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, int d, double sigma_color,
+                      double sigma_space, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && out && bgr != out, "null or aliased image pointer");
+    CVB_REQUIRE(d == 9, "bilateral diameter %d unsupported: the reference path uses d=9 (frame_enhancer.py:131)", d);
+    return launch_fused(h, bgr, n, H, W, false, true, false, nullptr, nullptr, sigma_color, sigma_space, out, nullptr);
+}
+int cvb_sharpen_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && out && bgr != out, "null or aliased image pointer");
+    return launch_fused(h, bgr, n, H, W, false, false, true, nullptr, nullptr, 0, 0, out, nullptr);
+}
+int cvb_normalize_dev(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C, uint8_t *out, int32_t *minmax_out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(src && out && C >= 1 && C <= 4, "null image pointer or bad channel count");
+    if (!minmax_out) CVB_TRY(cvb_ws(h, h->ws_minmax, sizeof(int32_t) * 2 * n, (void **)&minmax_out));
+    const long bytes = (long)H * W * C;
+    CVB_TRY(launch_minmax(h, src, n, bytes, minmax_out));
+    return launch_normalize(h, src, n, bytes, minmax_out, out);
+}
+int cvb_gray_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *gray)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && gray, "null image pointer");
+    return launch_gray(h, bgr, (long)n * H * W, gray);
+}
+int cvb_gaussian_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, int ksize, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(plane && out && plane != out, "null or aliased image pointer");
+    return launch_gaussian(h, plane, n, H, W, ksize, out);
+}
+
+static int analysis_tail(cvb_handle *h, const uint8_t *src, const int32_t *minmax, int n, int H, int W,
+                         uint8_t *enhanced, uint8_t *gray, uint8_t *binary, uint8_t *blurred, int32_t *otsu_t,
+                         int32_t *hist)
+{
+    const long npx = (long)H * W;
+    const bool want_bin = binary != nullptr || otsu_t != nullptr;
+    if (want_bin) {
+        if (!blurred) CVB_TRY(cvb_ws(h, h->ws_blur, (size_t)n * npx, (void **)&blurred));
+        if (!hist) CVB_TRY(cvb_ws(h, h->ws_ohist, sizeof(int32_t) * 256 * n, (void **)&hist));
+        if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
+    }
+    CVB_TRY(launch_finish(h, src, n, H, W, minmax, enhanced, gray, blurred, want_bin ? hist : nullptr));
+    if (want_bin) {
+        CVB_TRY(launch_otsu(h, hist, n, npx, otsu_t));
+        if (binary) CVB_TRY(launch_threshold(h, blurred, n, npx, otsu_t, binary));
+    }
+    return CVB_OK;
+}
+
+int cvb_prepare_analysis_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *gray, uint8_t *binary,
+                             uint8_t *blurred, int32_t *otsu_t, int32_t *hist)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr != nullptr, "null image pointer");
+    return analysis_tail(h, bgr, nullptr, n, H, W, nullptr, gray, binary, blurred, otsu_t, hist);
+}
+
+static int check_enhance_params(const cvb_enhance_params *p)
+{
+    CVB_REQUIRE(p != nullptr, "null params");
+    CVB_REQUIRE(p->bilateral_d == 9, "bilateral diameter %d unsupported: the reference path uses d=9", p->bilateral_d);
+    return CVB_OK;
+}
+
+int cvb_process_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_enhance_params *p,
+                             uint8_t *enhanced)
+{
+    return cvb_enhance_dev(h, bgr, n, H, W, p, enhanced, nullptr, nullptr, nullptr);
+}
+
+int cvb_enhance_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_enhance_params *p,
+                    uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr != nullptr, "null image pointer");
+    CVB_TRY(check_enhance_params(p));
+    ClaheGeom g;
+    CVB_TRY(cvb_clahe_geom(H, W, p->clahe_clip_limit, p->tiles_x, p->tiles_y, &g));
+    const size_t fb = (size_t)H * W * 3;
+    WS(ws_minmax, int32_t, 2 * n, minmax);
+    WS(ws_sharp, uint8_t, fb * n, sharp);
+    int32_t *hist = nullptr;
+    uint8_t *lut = nullptr;
+    // pass 1: tile histograms (+ min/max reset), LUTs
+    CVB_TRY(clahe_tables(h, bgr, 1, n, H, W, g, &hist, &lut, minmax));
+    // pass 2: lighting -> bilateral -> sharpen (+ min/max)
+    CVB_TRY(launch_fused(h, bgr, n, H, W, true, true, true, &g, lut, p->sigma_color, p->sigma_space, sharp, minmax));
+    // pass 3/4: normalize -> gray -> blur -> Otsu -> mask
+    if (!enhanced && !gray && !binary && !otsu_t) return CVB_OK;
+    if (!gray && !binary && !otsu_t) return launch_normalize(h, sharp, n, (long)fb, minmax, enhanced);
+    return analysis_tail(h, sharp, minmax, n, H, W, enhanced, gray, binary, nullptr, otsu_t, nullptr);
+}
+
+int cvb_enhance(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_enhance_params *p, uint8_t *enhanced,
+                uint8_t *gray, uint8_t *binary, int32_t *otsu_t)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr != nullptr, "null image pointer");
+    const size_t npx = (size_t)H * W, fb = npx * 3;
+    WS(ws_in, uint8_t, fb * n, d_in);
+    uint8_t *d_enh = nullptr, *d_gray = nullptr, *d_bin = nullptr;
+    int32_t *d_otsu = nullptr;
+    if (enhanced) CVB_TRY(cvb_ws(h, h->ws_enh, fb * n, (void **)&d_enh));
+    if (gray) CVB_TRY(cvb_ws(h, h->ws_gray, npx * n, (void **)&d_gray));
+    if (binary) CVB_TRY(cvb_ws(h, h->ws_bin, npx * n, (void **)&d_bin));
+    if (binary || otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&d_otsu));
+    CVB_CHECK_CUDA(cudaMemcpyAsync(d_in, bgr, fb * n, cudaMemcpyHostToDevice, h->stream));
+    CVB_TRY(cvb_enhance_dev(h, d_in, n, H, W, p, d_enh, d_gray, d_bin, d_otsu));
+    if (enhanced) CVB_CHECK_CUDA(cudaMemcpyAsync(enhanced, d_enh, fb * n, cudaMemcpyDeviceToHost, h->stream));
+    if (gray) CVB_CHECK_CUDA(cudaMemcpyAsync(gray, d_gray, npx * n, cudaMemcpyDeviceToHost, h->stream));
+    if (binary) CVB_CHECK_CUDA(cudaMemcpyAsync(binary, d_bin, npx * n, cudaMemcpyDeviceToHost, h->stream));
+    if (otsu_t) CVB_CHECK_CUDA(cudaMemcpyAsync(otsu_t, d_otsu, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+
+// ---- warp ------------------------------------------------------------------------------------
+static int upload_inverse_mats(cvb_handle *h, const double *M9, int n_mats, double **d_out)
+{
+    std::vector<double> inv((size_t)n_mats * 9);
+    for (int i = 0; i < n_mats; ++i)
+        if (cvb_host_invert3(M9 + 9 * i, inv.data() + 9 * i) != CVB_OK) {
+            cvb_set_error("perspective matrix %d is singular", i);
+            return CVB_ERR_INVALID;
+        }
+    WS(ws_mats, double, (size_t)n_mats * 9, d_m);
+    CVB_CHECK_CUDA(cudaMemcpyAsync(d_m, inv.data(), sizeof(double) * 9 * n_mats, cudaMemcpyHostToDevice, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // `inv` dies at return
+    *d_out = d_m;
+    return CVB_OK;
+}
+
+int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *M9, int n_mats, int out_h,
+                 int out_w, uint8_t *warped)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && warped && M9, "null pointer");
+    CVB_REQUIRE(n_mats == 1 || n_mats == n, "n_mats must be 1 or n");
+    CVB_REQUIRE(out_h >= 1 && out_w >= 1 && out_h <= 32768 && out_w <= 32768, "bad output size");
+    double *d_m = nullptr;
+    CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
+    return launch_warp(h, bgr, n, H, W, d_m, n_mats, out_h, out_w, warped);
+}
+
+// ---- per-square ---------------------------------------------------------------------------------
+int cvb_state_create(cvb_handle *h, int n_streams, int BH, int BW, cvb_state **out)
+{
+    REQ_H(h);
+    CVB_REQUIRE(out && n_streams >= 1 && BH >= 1 && BW >= 1, "bad state shape");
+    *out = nullptr;
+    cvb_state *s = new cvb_state();
+    s->h = h; s->n_streams = n_streams; s->BH = BH; s->BW = BW;
+    const size_t px = (size_t)n_streams * BH * BW;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&s->pd_ref, px);
+    if (e == cudaSuccess) e = cudaMalloc(&s->pd_cur, px);
+    if (e == cudaSuccess) e = cudaMalloc(&s->flags, px);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cd_mean, px * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s->cd_var, px * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->flags, 0, px, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->pd_ref, 0, px, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->pd_cur, 0, px, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->cd_mean, 0, px * sizeof(float), h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->cd_var, 0, px * sizeof(float), h->stream);
+    if (e != cudaSuccess) {
+        cvb_set_error("state allocation failed: %s", cudaGetErrorString(e));
+        cvb_state_destroy(s);
+        return CVB_ERR_CUDA;
+    }
+    *out = s;
+    return CVB_OK;
+}
+void cvb_state_destroy(cvb_state *s)
+{
+    if (!s) return;
+    if (s->h) cudaStreamSynchronize(s->h->stream);
+    cudaFree(s->pd_ref); cudaFree(s->pd_cur); cudaFree(s->flags); cudaFree(s->cd_mean); cudaFree(s->cd_var);
+    delete s;
+}
+
+static int state_plane(cvb_state *s, int stream, int plane, void **p, size_t *bytes)
+{
+    CVB_REQUIRE(s != nullptr, "null state");
+    CVB_REQUIRE(stream >= 0 && stream < s->n_streams, "stream slot %d out of range", stream);
+    const size_t px = (size_t)s->BH * s->BW, o = (size_t)stream * px;
+    switch (plane) {
+    case 0: *p = s->pd_ref + o; *bytes = px; break;
+    case 1: *p = s->cd_mean + o; *bytes = px * 4; break;
+    case 2: *p = s->cd_var + o; *bytes = px * 4; break;
+    case 3: *p = s->pd_cur + o; *bytes = px; break;
+    case 4: *p = s->flags + o; *bytes = px; break;
+    default: cvb_set_error("unknown state plane %d", plane); return CVB_ERR_INVALID;
+    }
+    return CVB_OK;
+}
+int cvb_state_get(cvb_handle *h, cvb_state *s, int stream, int plane, void *host_out)
+{
+    REQ_H(h);
+    void *p; size_t bytes;
+    CVB_TRY(state_plane(s, stream, plane, &p, &bytes));
+    CVB_CHECK_CUDA(cudaMemcpyAsync(host_out, p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+int cvb_state_set(cvb_handle *h, cvb_state *s, int stream, int plane, const void *host_in)
+{
+    REQ_H(h);
+    void *p; size_t bytes;
+    CVB_TRY(state_plane(s, stream, plane, &p, &bytes));
+    CVB_CHECK_CUDA(cudaMemcpyAsync(p, host_in, bytes, cudaMemcpyHostToDevice, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+int cvb_state_reset(cvb_handle *h, cvb_state *s, int stream)
+{
+    REQ_H(h);
+    CVB_REQUIRE(s != nullptr && stream < s->n_streams, "bad state / stream");
+    return launch_state_reset(h, s, stream);
+}
+
+// rects/select -> device, masks per distinct shape (cached on the handle by content)
+struct RectCache {
+    std::vector<cvb_rect> rects;
+    std::vector<uint8_t> select;
+    bool has_select = false;
+    int max_px = 0;
+    size_t mask_bytes = 0;
+};
+static std::map<cvb_handle *, RectCache> g_rect_cache;
+} // extern "C" (paused: C++ linkage for the helper below)
+static void drop_rect_cache(cvb_handle *h) { g_rect_cache.erase(h); }
+extern "C" {
+
+static int stage_rects(cvb_handle *h, const cvb_rect *rects, int n_sq, const uint8_t *select, int BH, int BW,
+                       cvb_rect **d_rects, int32_t **d_ofs, uint8_t **d_masks, uint8_t **d_select, int *max_px)
+{
+    CVB_REQUIRE(rects != nullptr && n_sq >= 1 && n_sq <= 65535, "bad rect list");
+    for (int i = 0; i < n_sq; ++i)
+        CVB_REQUIRE(rects[i].w >= 1 && rects[i].h >= 1 && rects[i].x >= 0 && rects[i].y >= 0 &&
+                        rects[i].x + rects[i].w <= BW && rects[i].y + rects[i].h <= BH,
+                    "square %d (%d,%d %dx%d) outside the %dx%d board", i, rects[i].x, rects[i].y, rects[i].w,
+                    rects[i].h, BW, BH);
+    RectCache &c = g_rect_cache[h];
+    const bool same_rects = (int)c.rects.size() == n_sq && memcmp(c.rects.data(), rects, sizeof(cvb_rect) * n_sq) == 0 &&
+                            h->ws_rects.p != nullptr;
+    const bool same_sel = same_rects && c.has_select == (select != nullptr) &&
+                          (!select || memcmp(c.select.data(), select, n_sq) == 0);
+    const size_t ofs_bytes = sizeof(int32_t) * n_sq, rect_bytes = sizeof(cvb_rect) * n_sq;
+    if (!same_rects) {
+        std::map<int, int32_t> shape_ofs;
+        std::vector<int32_t> ofs(n_sq);
+        std::vector<uint8_t> masks;
+        int mx = 0;
+        for (int i = 0; i < n_sq; ++i) {
+            const int key = (rects[i].h << 16) | rects[i].w;
+            auto it = shape_ofs.find(key);
+            if (it == shape_ofs.end()) {
+                const size_t o = masks.size();
+                masks.resize(o + (size_t)rects[i].h * rects[i].w);
+                cvb_host_square_masks(rects[i].h, rects[i].w, masks.data() + o);
+                it = shape_ofs.emplace(key, (int32_t)o).first;
+            }
+            ofs[i] = it->second;
+            mx = std::max(mx, rects[i].h * rects[i].w);
+        }
+        uint8_t *d_r = nullptr, *d_m = nullptr;
+        CVB_TRY(cvb_ws(h, h->ws_rects, rect_bytes + ofs_bytes, (void **)&d_r));
+        CVB_TRY(cvb_ws(h, h->ws_masks, masks.size(), (void **)&d_m));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(d_r, rects, rect_bytes, cudaMemcpyHostToDevice, h->stream));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(d_r + rect_bytes, ofs.data(), ofs_bytes, cudaMemcpyHostToDevice, h->stream));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(d_m, masks.data(), masks.size(), cudaMemcpyHostToDevice, h->stream));
+        CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+        c.rects.assign(rects, rects + n_sq);
+        c.max_px = mx;
+        c.mask_bytes = masks.size();
+    }
+    if (!same_sel) {
+        c.has_select = select != nullptr;
+        if (select) {
+            uint8_t *d_s = nullptr;
+            CVB_TRY(cvb_ws(h, h->ws_select, n_sq, (void **)&d_s));
+            CVB_CHECK_CUDA(cudaMemcpyAsync(d_s, select, n_sq, cudaMemcpyHostToDevice, h->stream));
+            CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+            c.select.assign(select, select + n_sq);
+        }
+    }
+    *d_rects = (cvb_rect *)h->ws_rects.p;
+    *d_ofs = (int32_t *)((uint8_t *)h->ws_rects.p + rect_bytes);
+    *d_masks = (uint8_t *)h->ws_masks.p;
+    *d_select = select ? (uint8_t *)h->ws_select.p : nullptr;
+    *max_px = c.max_px;
+    return CVB_OK;
+}
+
+static int squares_impl(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C, const cvb_rect *rects,
+                        int n_sq, const uint8_t *select, cvb_state *state, int stream0, const cvb_square_params *p,
+                        cvb_square_stats *stats)
+{
+    CVB_REQUIRE(boards != nullptr && p != nullptr, "null pointer");
+    CVB_REQUIRE(C == 1 || C == 3, "boards must have 1 or 3 channels, got %d", C);
+    CVB_REQUIRE(n >= 1 && n <= 65535 && BH >= 1 && BW >= 1, "bad board batch");
+    const int state_ops = CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE;
+    if (p->ops & state_ops) {
+        if (!state) { cvb_set_error("ops 0x%x need a cvb_state", p->ops); return CVB_ERR_STATE; }
+    }
+    if (state) {
+        if (state->BH != BH || state->BW != BW) {
+            cvb_set_error("state is %dx%d but boards are %dx%d", state->BH, state->BW, BH, BW);
+            return CVB_ERR_STATE;
+        }
+        if (stream0 < 0 || stream0 + n > state->n_streams) {
+            cvb_set_error("stream slots %d..%d outside the state's %d", stream0, stream0 + n - 1, state->n_streams);
+            return CVB_ERR_STATE;
+        }
+    }
+    int pd_q[31] = {0}, cd_q[31] = {0};
+    if (cvb_host_gaussian_q8(p->pd_blur, pd_q) != CVB_OK || cvb_host_gaussian_q8(p->cd_blur, cd_q) != CVB_OK) {
+        cvb_set_error("blur kernels must be odd and <= 31 (pd %d, cd %d)", p->pd_blur, p->cd_blur);
+        return CVB_ERR_INVALID;
+    }
+    cvb_rect *d_rects; int32_t *d_ofs; uint8_t *d_masks, *d_select; int max_px;
+    CVB_TRY(stage_rects(h, rects, n_sq, select, BH, BW, &d_rects, &d_ofs, &d_masks, &d_select, &max_px));
+    return launch_squares(h, boards, n, BH, BW, C, d_rects, d_ofs, d_masks, n_sq, max_px, d_select, state, stream0, *p,
+                          pd_q, cd_q, stats);
+}
+
+int cvb_squares_dev(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C, const cvb_rect *rects, int n_sq,
+                    const uint8_t *select, cvb_state *state, int stream0, const cvb_square_params *p,
+                    cvb_square_stats *stats)
+{
+    REQ_H(h);
+    return squares_impl(h, boards, n, BH, BW, C, rects, n_sq, select, state, stream0, p, stats);
+}
+
+// ---- whole path ----------------------------------------------------------------------------------
+int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,
+                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select,
+                     cvb_state *state, int stream0, uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t,
+                     uint8_t *warped, cvb_square_stats *stats)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && p && M9 && rects, "null pointer");
+    CVB_REQUIRE(n_mats == 1 || n_mats == n, "n_mats must be 1 or n");
+    const int S = p->board_size;
+    CVB_REQUIRE(S >= 8 && S <= 8192, "bad board_size %d", S);
+    const size_t npx = (size_t)H * W, fb = npx * 3;
+    if (!enhanced) CVB_TRY(cvb_ws(h, h->ws_enh, fb * n, (void **)&enhanced));
+    if (!gray) CVB_TRY(cvb_ws(h, h->ws_gray, npx * n, (void **)&gray));
+    if (!binary) CVB_TRY(cvb_ws(h, h->ws_bin, npx * n, (void **)&binary));
+    if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
+    if (!warped) CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * n, (void **)&warped));
+    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
+    double *d_m = nullptr;
+    CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
+    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_m, n_mats, S, S, warped));
+    return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
+}
+
+int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p, const double *M9,
+                 int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state, int stream0,
+                 int32_t *otsu_t, cvb_square_stats *stats)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr != nullptr && n_sq >= 1, "null image pointer / no squares");
+    const size_t fb = (size_t)H * W * 3;
+    WS(ws_in, uint8_t, fb * n, d_in);
+    WS(ws_stats, cvb_square_stats, (size_t)n * n_sq, d_stats);
+    int32_t *d_otsu = nullptr;
+    CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&d_otsu));
+    CVB_CHECK_CUDA(cudaMemcpyAsync(d_in, bgr, fb * n, cudaMemcpyHostToDevice, h->stream));
+    CVB_TRY(cvb_pipeline_dev(h, d_in, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, nullptr, nullptr,
+                             nullptr, d_otsu, nullptr, d_stats));
+    if (stats)
+        CVB_CHECK_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(cvb_square_stats) * (size_t)n * n_sq,
+                                       cudaMemcpyDeviceToHost, h->stream));
+    if (otsu_t) CVB_CHECK_CUDA(cudaMemcpyAsync(otsu_t, d_otsu, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,842 @@
+// frame_enhancer hot path as sm_100a kernels.
+//
+//   pass 1  k_tile_hist      BGR -> L (LUT) -> 8x8 tile histograms        (read 3N)
+//           k_clahe_lut      clip / redistribute / scan -> 64 LUTs         (tiny)
+//   pass 2  k_fused          LAB, CLAHE blend, LAB->BGR into a smem halo
+//                            tile; bilateral d=9 from smem; 3x3 sharpen;
+//                            global min/max                                (read 3N, write 3N)
+//   pass 3  k_finish         normalize, gray, blur 5x5, Otsu histogram     (read 3N, write 5N)
+//           k_otsu           f64 Otsu scan                                 (tiny)
+//   pass 4  k_threshold      binary mask                                   (read N, write N)
+//
+// Reference: frame_enhancer.py:101-181 (ImageEnhancerPython) and its Cython
+// twin src/cython/frame_enhancer_cython.pyx:86-153, which call cv2 for every
+// stage; the arithmetic restated here is OpenCV 4.13's (file names per kernel).
+// Compiled with -fmad=false: every fused multiply-add below is explicit.
+#include "cvb_device.cuh"
+#include <cfloat>
+
+#define LAUNCH_CHECK(h)                                  \
+    do {                                                 \
+        (h)->launches++;                                 \
+        CVB_CHECK_CUDA(cudaGetLastError());              \
+    } while (0)
+
+int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g)
+{
+    CVB_REQUIRE(tx >= 1 && ty >= 1 && tx <= 16 && ty <= 16, "CLAHE tile grid %dx%d unsupported (1..16)", tx, ty);
+    CVB_REQUIRE(H >= 1 && W >= 1, "empty image");
+    g->tiles_x = tx; g->tiles_y = ty;
+    g->ext_w = W; g->ext_h = H;
+    if (W % tx != 0 || H % ty != 0) {  // clahe.cpp pads both axes, even one that divides
+        g->ext_w = W + (tx - W % tx);
+        g->ext_h = H + (ty - H % ty);
+    }
+    g->tile_w = g->ext_w / tx; g->tile_h = g->ext_h / ty;
+    const int area = g->tile_w * g->tile_h;
+    g->clip = 0;
+    if (clip_limit > 0.0) {
+        g->clip = (int)(clip_limit * area / 256);
+        if (g->clip < 1) g->clip = 1;
+    }
+    g->lut_scale = (float)255 / (float)area;
+    g->inv_tw = 1.0f / (float)g->tile_w;
+    g->inv_th = 1.0f / (float)g->tile_h;
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pointwise colour conversions (stage-isolated API; the hot path uses k_fused)
+// ---------------------------------------------------------------------------------------
+template <bool FWD>
+__global__ void __launch_bounds__(256) k_lab_pointwise(const uint8_t *__restrict__ src, long npx,
+                                                       const CvbTables *__restrict__ tabs, uint8_t *__restrict__ dst)
+{
+    __shared__ SmemColorTables st;
+    load_color_tables(&st, tabs);
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long)gridDim.x * blockDim.x) {
+        const int c0 = src[3 * i], c1 = src[3 * i + 1], c2 = src[3 * i + 2];
+        if (FWD) {
+            int L, A, B;
+            bgr2lab_px(&st, c0, c1, c2, L, A, B);
+            dst[3 * i] = (uint8_t)L; dst[3 * i + 1] = (uint8_t)A; dst[3 * i + 2] = (uint8_t)B;
+        } else {
+            const uint32_t q = lab2bgr_px(&st, c0, c1, c2);
+            dst[3 * i] = (uint8_t)q; dst[3 * i + 1] = (uint8_t)(q >> 8); dst[3 * i + 2] = (uint8_t)(q >> 16);
+        }
+    }
+}
+// blocks along x for a grid-stride streaming kernel: enough for `vecs` 16-byte
+// vectors at 256 per block, capped so that the whole launch stays near `cap`
+static int stream_blocks(long vecs, int cap)
+{
+    long b = (vecs + 255) / 256 + 1;
+    if (cap < 1) cap = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+static int grid_for(cvb_handle *h, long items, int per_block)
+{
+    long b = (items + per_block - 1) / per_block;
+    long cap = (long)h->sm_count * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+int launch_bgr2lab(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *lab)
+{
+    k_lab_pointwise<true><<<grid_for(h, npx, 256), 256, 0, h->stream>>>(bgr, npx, h->d_tables, lab);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr)
+{
+    k_lab_pointwise<false><<<grid_for(h, npx, 256), 256, 0, h->stream>>>(lab, npx, h->d_tables, bgr);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 1: per-tile histograms of L (CLAHE_CalcLut_Body, histogram part)
+//   grid = (tiles, row-splits, frames); warp-private 256-bin histograms in smem.
+//   Tiles are laid over the REFLECT_101-extended image (clahe.cpp), so right /
+//   bottom tiles of non-divisible sizes read mirrored pixels.
+// ---------------------------------------------------------------------------------------
+template <bool FROM_BGR>
+__global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ src, int H, int W, ClaheGeom g,
+                                                   const CvbTables *__restrict__ tabs, int32_t *__restrict__ hist,
+                                                   int32_t *__restrict__ minmax_init)
+{
+    __shared__ int s_hist[8][256];
+    __shared__ int s_tY[3][256];          // per-channel contribution to the Y index numerator
+    __shared__ uint8_t s_ltab[2048];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tile = blockIdx.x, tx = tile % g.tiles_x, ty = tile / g.tiles_x;
+    const int frame = blockIdx.z;
+    for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+    if (FROM_BGR) {
+        const int gv = tabs->gamma[tid];
+        s_tY[0][tid] = gv * 296; s_tY[1][tid] = gv * 2929; s_tY[2][tid] = gv * 871;
+        for (int i = tid; i < 2048; i += 256) s_ltab[i] = tabs->ltab[i];
+    }
+    if (minmax_init && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        minmax_init[2 * frame] = 255; minmax_init[2 * frame + 1] = 0;
+    }
+    __syncthreads();
+    const int rows_per = (g.tile_h + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, g.tile_h);
+    const uint8_t *img = src + (size_t)frame * H * W * (FROM_BGR ? 3 : 1);
+    const int npx = (r1 - r0) * g.tile_w;
+    int *my = s_hist[warp];
+    for (int i = tid; i < npx; i += 256) {
+        const int ry = i / g.tile_w, rx = i - ry * g.tile_w;
+        const int sy = reflect101(ty * g.tile_h + r0 + ry, H), sx = reflect101(tx * g.tile_w + rx, W);
+        int L;
+        if (FROM_BGR) {
+            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
+            L = s_ltab[(s_tY[0][p[0]] + s_tY[1][p[1]] + s_tY[2][p[2]] + 2048) >> 12];
+        } else {
+            L = img[(size_t)sy * W + sx];
+        }
+        atomicAdd(&my[L], 1);
+    }
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_hist[w][tid];
+    if (tot) atomicAdd(&hist[((size_t)frame * g.tiles_x * g.tiles_y + tile) * 256 + tid], tot);
+}
+int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W, const ClaheGeom &g,
+                     int32_t *hist, int32_t *minmax_init)
+{
+    const int tiles = g.tiles_x * g.tiles_y;
+    CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * tiles * (size_t)n, h->stream));
+    // enough blocks per frame to fill the machine at n == 1, fewer splits for big batches
+    int splits = (4 * h->sm_count + tiles * n - 1) / (tiles * n);
+    splits = max(1, min(splits, (g.tile_h + 7) / 8));
+    dim3 grid(tiles, splits, n);
+    if (from_bgr) k_tile_hist<true><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
+    else k_tile_hist<false><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// clip, redistribute, prefix-sum, scale: one block per tile, one thread per bin
+__global__ void __launch_bounds__(256) k_clahe_lut(const int32_t *__restrict__ hist, ClaheGeom g, uint8_t *__restrict__ lut)
+{
+    __shared__ int s_part[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t base = (size_t)blockIdx.x * 256;
+    int v = hist[base + tid];
+    if (g.clip > 0) {
+        int over = max(v - g.clip, 0);
+        v -= over;
+        over = warp_sum(over);
+        if (lane == 0) s_part[warp] = over;
+        __syncthreads();
+        int clipped = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) clipped += s_part[w];
+        const int batch = clipped / 256;
+        int resid = clipped - batch * 256;
+        v += batch;
+        if (resid != 0) {
+            // for (i = 0; i < 256 && resid > 0; i += step, --resid) h[i]++
+            const int step = max(256 / resid, 1);
+            if (tid % step == 0 && tid / step < resid) v += 1;
+        }
+        __syncthreads();
+    }
+    // inclusive scan over 256 bins
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_part[warp] = x;
+    __syncthreads();
+    int add = 0;
+    for (int w = 0; w < warp; ++w) add += s_part[w];
+    x += add;
+    lut[base + tid] = (uint8_t)round_u8(__fmul_rn((float)x, g.lut_scale));
+}
+int launch_clahe_lut(cvb_handle *h, const int32_t *hist, int n, const ClaheGeom &g, uint8_t *lut)
+{
+    k_clahe_lut<<<g.tiles_x * g.tiles_y * n, 256, 0, h->stream>>>(hist, g, lut);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// CLAHE interpolation on a plain u8 plane (stage-isolated API)
+__global__ void __launch_bounds__(256) k_clahe_apply_plane(const uint8_t *__restrict__ src, int H, int W, ClaheGeom g,
+                                                           const uint8_t *__restrict__ lut, uint8_t *__restrict__ dst)
+{
+    const int frame = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const size_t o = (size_t)frame * H * W + (size_t)y * W + x;
+    const ClaheAxis ax = clahe_axis(x, g.inv_tw, g.tiles_x), ay = clahe_axis(y, g.inv_th, g.tiles_y);
+    dst[o] = (uint8_t)clahe_interp(lut + (size_t)frame * g.tiles_x * g.tiles_y * 256, g.tiles_x, ax, ay, src[o]);
+}
+int launch_clahe_apply_plane(cvb_handle *h, const uint8_t *src, int n, int H, int W, const ClaheGeom &g,
+                             const uint8_t *lut, uint8_t *dst)
+{
+    dim3 grid((W + 63) / 64, (H + 3) / 4, n);
+    k_clahe_apply_plane<<<grid, 256, 0, h->stream>>>(src, H, W, g, lut, dst);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 2: the fused tile kernel.
+//   A  stage the (optionally lighting-corrected) pixels of the tile plus halo in
+//      shared memory as packed BGRx words; out-of-image positions are filled by
+//      REFLECT_101, i.e. exactly the copyMakeBorder image bilateralFilter sees.
+//   B  bilateral d=9 (bilateral_filter.dispatch.cpp / .simd.hpp): circular support
+//      r<=4 (49 taps), weight = space[k] * color[|db|+|dg|+|dr|], taps accumulated
+//      in row-major order with fmaf, result = rint(sum * (1/wsum)).  Each thread
+//      owns runs of 4 adjacent pixels; a row of the window is three LDS.128.
+//   C  3x3 sharpen 10*c - sum9, saturate (filter2D, REFLECT_101 of the *filtered*
+//      image: mirrored neighbours index already-computed B pixels) + min/max.
+// ---------------------------------------------------------------------------------------
+struct FusedArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    int H, W;
+    const CvbTables *tabs;
+    const uint8_t *lut;       // CLAHE LUTs of all frames (LIGHT)
+    ClaheGeom g;
+    const float *color;       // 768 colour weights (device)
+    float sw[81];             // spatial weights [dy+4][dx+4]
+    int32_t *minmax;          // per frame {min,max} or null
+};
+
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
+struct FusedCfg {
+    static constexpr int BX = SHARP ? 2 : 0, BY = SHARP ? 1 : 0;   // B halo around the tile
+    static constexpr int BW = TW + 2 * BX, BH = TH + 2 * BY;
+    static constexpr int AR = BIL ? 4 : 0;
+    static constexpr int AW = BW + 2 * AR, AH = BH + 2 * AR;
+    static constexpr int RUNS = BW / 4;
+    static_assert(TW % 4 == 0 && BW % 4 == 0 && AW % 4 == 0, "runs of 4 / LDS.128 alignment");
+    static constexpr size_t smem_bytes =
+        (size_t)AW * AH * 4 + (BIL ? (size_t)BW * BH * 4 + 768 * 4 : 0) + (LIGHT ? sizeof(SmemColorTables) : 0);
+};
+
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
+__global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
+{
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP>;
+    constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *sB = BIL ? sA + AW * AH : sA;
+    float *sColor = reinterpret_cast<float *>(sB + (BIL ? BW * BH : 0));
+    SmemColorTables *sTab = reinterpret_cast<SmemColorTables *>(smem_raw + (size_t)AW * AH * 4 +
+                                                                (BIL ? (size_t)BW * BH * 4 + 768 * 4 : 0));
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int H = a.H, W = a.W;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int bx0 = x0 - Cfg::BX, by0 = y0 - Cfg::BY, ax0 = bx0 - AR, ay0 = by0 - AR;
+    const uint8_t *img = a.src + (size_t)frame * H * W * 3;
+
+    if (LIGHT) load_color_tables(sTab, a.tabs);
+    if (BIL)
+        for (int i = tid; i < 768; i += 256) sColor[i] = __ldg(a.color + i);
+    if (LIGHT) __syncthreads();
+
+    // ---- A ----
+    {
+        const uint8_t *lut = LIGHT ? a.lut + (size_t)frame * a.g.tiles_x * a.g.tiles_y * 256 : nullptr;
+        for (int i = tid; i < AW * AH; i += 256) {
+            const int ly = i / AW, lx = i - ly * AW;
+            const int sy = reflect101(ay0 + ly, H), sx = reflect101(ax0 + lx, W);
+            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
+            const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
+            uint32_t q;
+            if (LIGHT) {
+                int L, A, B;
+                bgr2lab_px(sTab, c0, c1, c2, L, A, B);
+                const ClaheAxis ax = clahe_axis(sx, a.g.inv_tw, a.g.tiles_x), ay = clahe_axis(sy, a.g.inv_th, a.g.tiles_y);
+                L = clahe_interp(lut, a.g.tiles_x, ax, ay, L);
+                q = lab2bgr_px(sTab, L, A, B);
+            } else {
+                q = pack_bgr(c0, c1, c2);
+            }
+            sA[i] = q;
+        }
+    }
+    __syncthreads();
+
+    // ---- B ----
+    if (BIL) {
+        constexpr int RUNS = Cfg::RUNS;
+        for (int item = tid; item < BH * RUNS; item += 256) {
+            const int row = item / RUNS, r4 = (item - row * RUNS) * 4;
+            const int Y = by0 + row, X = bx0 + r4;
+            if (Y < 0 || Y >= H || X + 3 < 0 || X >= W) continue;
+            float wsum[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f},
+                  sr[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t ctr[4];
+            {
+                const uint4 c = *reinterpret_cast<const uint4 *>(sA + (row + 4) * AW + r4 + 4);
+                ctr[0] = c.x; ctr[1] = c.y; ctr[2] = c.z; ctr[3] = c.w;
+            }
+#pragma unroll
+            for (int dy = -4; dy <= 4; ++dy) {
+                const uint32_t *rowp = sA + (row + 4 + dy) * AW + r4;
+                uint32_t px[12];
+                float fb[12], fg[12], fr[12];
+                // columns r4 .. r4+11 of the A tile hold image x = X-4 .. X+7
+                // first needed column: 4 - (largest |dx| on this row of the disc)
+                const int ady = dy < 0 ? -dy : dy;
+                const int lo = ady == 4 ? 4 : ady == 3 ? 2 : ady >= 1 ? 1 : 0;
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    if (v != 1 && lo >= 4) continue;                 // |dy| == 4 needs only the middle quad
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rowp + 4 * v);
+                    px[4 * v] = q.x; px[4 * v + 1] = q.y; px[4 * v + 2] = q.z; px[4 * v + 3] = q.w;
+                }
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    if (c < lo || c > 11 - lo) continue;
+                    fb[c] = (float)(px[c] & 0xffu);
+                    fg[c] = (float)((px[c] >> 8) & 0xffu);
+                    fr[c] = (float)((px[c] >> 16) & 0xffu);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int dx = -4; dx <= 4; ++dx) {
+                        if (dy * dy + dx * dx > 16) continue;
+                        const int c = j + 4 + dx;
+                        const float w = __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sColor[__vsadu4(px[c], ctr[j])]);
+                        wsum[j] = __fadd_rn(wsum[j], w);
+                        sb[j] = __fmaf_rn(fb[c], w, sb[j]);
+                        sg[j] = __fmaf_rn(fg[c], w, sg[j]);
+                        sr[j] = __fmaf_rn(fr[c], w, sr[j]);
+                    }
+                }
+            }
+            uint4 o;
+            uint32_t *op = &o.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float inv = __fdiv_rn(1.0f, wsum[j]);
+                op[j] = pack_bgr(round_u8(__fmul_rn(sb[j], inv)), round_u8(__fmul_rn(sg[j], inv)),
+                                 round_u8(__fmul_rn(sr[j], inv)));
+            }
+            *reinterpret_cast<uint4 *>(sB + row * BW + r4) = o;
+        }
+        __syncthreads();
+    }
+
+    // ---- C ----
+    int vmin = 255, vmax = 0;
+    uint8_t *out = a.dst + (size_t)frame * H * W * 3;
+    const bool fast = (W % 4 == 0) && (x0 + TW <= W) && ((reinterpret_cast<uintptr_t>(a.dst) & 3) == 0);
+    constexpr int GROUPS = TW / 4;
+    for (int item = tid; item < TH * GROUPS; item += 256) {
+        const int ty = item / GROUPS, tx4 = (item - ty * GROUPS) * 4;
+        const int Y = y0 + ty;
+        if (Y >= H) break;
+        uint32_t res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int X = x0 + tx4 + j;
+            uint32_t q = 0;
+            if (X < W) {
+                if (SHARP) {
+                    const int ym = reflect101(Y - 1, H) - by0, yc = Y - by0, yp = reflect101(Y + 1, H) - by0;
+                    const int xm = reflect101(X - 1, W) - bx0, xc = X - bx0, xp = reflect101(X + 1, W) - bx0;
+                    uint32_t s02 = 0, s1 = 0;   // 16-bit lanes: (b, r) and (g)
+                    const int ys[3] = {ym, yc, yp}, xs[3] = {xm, xc, xp};
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            const uint32_t t = sB[ys[u] * BW + xs[v]];
+                            s02 += t & 0x00ff00ffu;
+                            s1 += (t >> 8) & 0xffu;
+                        }
+                    const uint32_t c = sB[yc * BW + xc];
+                    const int b = clamp_u8(10 * (int)(c & 0xff) - (int)(s02 & 0xffff));
+                    const int g = clamp_u8(10 * (int)((c >> 8) & 0xff) - (int)s1);
+                    const int r = clamp_u8(10 * (int)((c >> 16) & 0xff) - (int)(s02 >> 16));
+                    q = pack_bgr(b, g, r);
+                } else {
+                    q = sB[(Y - by0) * BW + (X - bx0)];
+                }
+                const int b = q & 0xff, g = (q >> 8) & 0xff, r = (q >> 16) & 0xff;
+                vmin = min(vmin, min(b, min(g, r)));
+                vmax = max(vmax, max(b, max(g, r)));
+            }
+            res[j] = q;
+        }
+        uint8_t *o = out + ((size_t)Y * W + x0 + tx4) * 3;
+        if (fast) {
+            // 4 pixels = 12 bytes = 3 aligned words
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+            o32[0] = (res[0] & 0xffffffu) | (res[1] << 24);
+            o32[1] = ((res[1] >> 8) & 0xffffu) | (res[2] << 16);
+            o32[2] = ((res[2] >> 16) & 0xffu) | (res[3] << 8);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x0 + tx4 + j < W) {
+                    o[3 * j] = (uint8_t)res[j]; o[3 * j + 1] = (uint8_t)(res[j] >> 8); o[3 * j + 2] = (uint8_t)(res[j] >> 16);
+                }
+        }
+    }
+    if (a.minmax) {
+        vmin = warp_min(vmin); vmax = warp_max(vmax);
+        if ((tid & 31) == 0) {
+            atomicMin(a.minmax + 2 * frame, vmin);
+            atomicMax(a.minmax + 2 * frame + 1, vmax);
+        }
+    }
+}
+
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
+static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
+{
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
+        attr_done = true;
+    }
+    dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, n);
+    kern<<<grid, 256, Cfg::smem_bytes, h->stream>>>(a);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool light, bool bilateral, bool sharpen,
+                 const ClaheGeom *g, const uint8_t *lut, double sigma_color, double sigma_space, uint8_t *out,
+                 int32_t *minmax)
+{
+    FusedArgs a;
+    a.src = src; a.dst = out; a.H = H; a.W = W; a.tabs = h->d_tables; a.lut = lut; a.minmax = minmax;
+    a.color = nullptr;
+    if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
+    memset(a.sw, 0, sizeof a.sw);
+    if (bilateral) {
+        if (h->color_sigma != sigma_color || !h->d_color) {
+            float color[768];
+            cvb_host_bilateral_tables(sigma_color, sigma_space, color, nullptr);
+            if (!h->d_color) CVB_CHECK_CUDA(cudaMalloc(&h->d_color, sizeof color));
+            // pageable source: the copy is staged before the call returns
+            CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, color, sizeof color, cudaMemcpyHostToDevice, h->stream));
+            CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+            h->color_sigma = sigma_color;
+        }
+        cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
+        a.color = h->d_color;
+    }
+    constexpr int TW = 60, TH = 30;
+    if (light && bilateral && sharpen) return launch_fused_t<TW, TH, true, true, true>(h, a, n);
+    if (!light && bilateral && !sharpen) return launch_fused_t<TW, TH, false, true, false>(h, a, n);
+    if (!light && !bilateral && sharpen) return launch_fused_t<TW, TH, false, false, true>(h, a, n);
+    if (!light && bilateral && sharpen) return launch_fused_t<TW, TH, false, true, true>(h, a, n);
+    if (light && !bilateral && !sharpen) return launch_fused_t<TW, TH, true, false, false>(h, a, n);
+    if (light && bilateral && !sharpen) return launch_fused_t<TW, TH, true, true, false>(h, a, n);
+    cvb_set_error("unsupported fused stage combination");
+    return CVB_ERR_INVALID;
+}
+int launch_correct_lighting(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const ClaheGeom &g,
+                            const uint8_t *lut, uint8_t *out)
+{
+    return launch_fused(h, bgr, n, H, W, true, false, false, &g, lut, 0, 0, out, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// S6 stand-alone: global min/max over all channels, then the 256-entry map
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_minmax_init(int32_t *minmax, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { minmax[2 * i] = 255; minmax[2 * i + 1] = 0; }
+}
+__global__ void __launch_bounds__(256) k_minmax(const uint8_t *__restrict__ src, long bytes, int32_t *__restrict__ minmax)
+{
+    const int frame = blockIdx.y;
+    const uint8_t *p = src + (size_t)frame * bytes;
+    int lo = 255, hi = 0;
+    const long nvec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? bytes / 16 : 0;
+    const uint4 *pv = reinterpret_cast<const uint4 *>(p);
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+        const uint4 q = __ldg(pv + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // bytewise min/max of the word against the running packed extrema
+            lo = min(lo, (int)min(min(w[k] & 0xff, (w[k] >> 8) & 0xff), min((w[k] >> 16) & 0xff, w[k] >> 24)));
+            hi = max(hi, (int)max(max(w[k] & 0xff, (w[k] >> 8) & 0xff), max((w[k] >> 16) & 0xff, w[k] >> 24)));
+        }
+    }
+    for (long i = nvec * 16 + (long)blockIdx.x * 256 + threadIdx.x; i < bytes; i += (long)gridDim.x * 256) {
+        const int v = p[i];
+        lo = min(lo, v); hi = max(hi, v);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(minmax + 2 * frame, lo);
+        atomicMax(minmax + 2 * frame + 1, hi);
+    }
+}
+int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, int32_t *minmax)
+{
+    k_minmax_init<<<(n + 255) / 256, 256, 0, h->stream>>>(minmax, n);
+    LAUNCH_CHECK(h);
+    int bx = stream_blocks(bytes_per_frame / 16, 8 * h->sm_count / (n > 0 ? n : 1));
+    dim3 grid(bx, n);
+    k_minmax<<<grid, 256, 0, h->stream>>>(src, bytes_per_frame, minmax);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+__global__ void __launch_bounds__(256) k_normalize(const uint8_t *__restrict__ src, long bytes,
+                                                   const int32_t *__restrict__ minmax, uint8_t *__restrict__ dst)
+{
+    __shared__ uint8_t s_map[256];
+    const int frame = blockIdx.y;
+    s_map[threadIdx.x] = (uint8_t)normalize_value(threadIdx.x, minmax[2 * frame], minmax[2 * frame + 1]);
+    __syncthreads();
+    const uint8_t *p = src + (size_t)frame * bytes;
+    uint8_t *o = dst + (size_t)frame * bytes;
+    const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+    const long nvec = al ? bytes / 16 : 0;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        uint32_t *w = &q.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = (uint32_t)s_map[w[k] & 0xff] | ((uint32_t)s_map[(w[k] >> 8) & 0xff] << 8) |
+                   ((uint32_t)s_map[(w[k] >> 16) & 0xff] << 16) | ((uint32_t)s_map[w[k] >> 24] << 24);
+        reinterpret_cast<uint4 *>(o)[i] = q;
+    }
+    for (long i = nvec * 16 + (long)blockIdx.x * 256 + threadIdx.x; i < bytes; i += (long)gridDim.x * 256)
+        o[i] = s_map[p[i]];
+}
+int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, const int32_t *minmax, uint8_t *out)
+{
+    int bx = stream_blocks(bytes_per_frame / 16, 16 * h->sm_count / (n > 0 ? n : 1));
+    dim3 grid(bx, n);
+    k_normalize<<<grid, 256, 0, h->stream>>>(src, bytes_per_frame, minmax, out);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// S7 stand-alone
+__global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ bgr, long npx, uint8_t *__restrict__ gray)
+{
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long)gridDim.x * 256)
+        gray[i] = (uint8_t)gray_px(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+}
+int launch_gray(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *gray)
+{
+    k_gray<<<grid_for(h, npx, 256), 256, 0, h->stream>>>(bgr, npx, gray);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// S8 stand-alone, any odd k <= 31: Q8 x Q8 fixed point (smooth.dispatch.cpp /
+// fixedpoint.inl.hpp), REFLECT_101.  64x16 tile + halo in shared memory.
+struct GaussK { int q[31]; int k; };
+__global__ void __launch_bounds__(256) k_gaussian(const uint8_t *__restrict__ src, int H, int W, GaussK gk,
+                                                  uint8_t *__restrict__ dst)
+{
+    constexpr int TWG = 64, THG = 16, RMAX = 15;
+    __shared__ uint8_t s_in[(THG + 2 * RMAX) * (TWG + 2 * RMAX)];
+    __shared__ uint16_t s_h[(THG + 2 * RMAX) * TWG];
+    const int r = gk.k / 2, aw = TWG + 2 * r, ah = THG + 2 * r;
+    const int frame = blockIdx.z, x0 = blockIdx.x * TWG, y0 = blockIdx.y * THG, tid = threadIdx.x;
+    const uint8_t *img = src + (size_t)frame * H * W;
+    for (int i = tid; i < aw * ah; i += 256) {
+        const int ly = i / aw, lx = i - ly * aw;
+        s_in[i] = img[(size_t)reflect101(y0 - r + ly, H) * W + reflect101(x0 - r + lx, W)];
+    }
+    __syncthreads();
+    for (int i = tid; i < ah * TWG; i += 256) {
+        const int ly = i / TWG, lx = i - ly * TWG;
+        uint32_t s = 0;
+        for (int j = 0; j < gk.k; ++j) s += (uint32_t)gk.q[j] * s_in[ly * aw + lx + j];
+        s_h[i] = (uint16_t)s;
+    }
+    __syncthreads();
+    for (int i = tid; i < THG * TWG; i += 256) {
+        const int ly = i / TWG, lx = i - ly * TWG;
+        const int X = x0 + lx, Y = y0 + ly;
+        if (X >= W || Y >= H) continue;
+        uint32_t s = 0;
+        for (int j = 0; j < gk.k; ++j) s += (uint32_t)gk.q[j] * s_h[(ly + j) * TWG + lx];
+        dst[(size_t)frame * H * W + (size_t)Y * W + X] = (uint8_t)((s + 32768u) >> 16);
+    }
+}
+int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, uint8_t *dst)
+{
+    GaussK gk;
+    memset(&gk, 0, sizeof gk);
+    if (cvb_host_gaussian_q8(ksize, gk.q) != CVB_OK) {
+        cvb_set_error("GaussianBlur ksize %d unsupported (odd, 1..31)", ksize);
+        return CVB_ERR_INVALID;
+    }
+    gk.k = ksize;
+    dim3 grid((W + 63) / 64, (H + 15) / 16, n);
+    k_gaussian<<<grid, 256, 0, h->stream>>>(src, H, W, gk, dst);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 128x16, halo 2.
+// Rows are staged through shared memory with 16-byte transfers on both the
+// read (sharpened frame) and the write (enhanced frame) side.
+// ---------------------------------------------------------------------------------------
+template <bool NORM>
+__global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src, int H, int W,
+                                                const int32_t *__restrict__ minmax, uint8_t *__restrict__ enhanced,
+                                                uint8_t *__restrict__ gray, uint8_t *__restrict__ blurred,
+                                                int32_t *__restrict__ hist)
+{
+    constexpr int FW = 128, FH = 16, R = 2, GW = FW + 2 * R, GH = FH + 2 * R;
+    constexpr int ROWB = GW * 3 + 16 + 12;               // staged bytes per row (+phase, padded to 16)
+    constexpr int ROWP = (ROWB + 15) / 16 * 16;
+    __shared__ __align__(16) uint8_t s_row[GH][ROWP];     // raw BGR rows (normalized in place for interior rows)
+    __shared__ __align__(16) uint8_t s_g[GH][GW + 12];    // gray with halo
+    __shared__ uint16_t s_h[GH][FW];                      // horizontal pass
+    __shared__ int s_hist[8][256];
+    __shared__ uint8_t s_map[256];
+    const int tid = threadIdx.x, frame = blockIdx.z;
+    const int x0 = blockIdx.x * FW, y0 = blockIdx.y * FH;
+    const size_t fo = (size_t)frame * H * W;
+    const uint8_t *img = src + fo * 3;
+    for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+    if (NORM) s_map[tid] = (uint8_t)normalize_value(tid, minmax[2 * frame], minmax[2 * frame + 1]);
+    // columns actually present in the image for this tile (+halo)
+    const int cx0 = max(x0 - R, 0), cx1 = min(x0 + FW + R, W);
+    const int span = (cx1 - cx0) * 3;
+    for (int ly = 0; ly < GH; ++ly) {
+        const int sy = reflect101(y0 - R + ly, H);
+        g2s_span(s_row[ly], img + ((size_t)sy * W + cx0) * 3, span, tid, 256);
+    }
+    __syncthreads();
+    // normalize in shared memory (bytes), then emit the enhanced rows of the interior
+    if (NORM) {
+        for (int ly = 0; ly < GH; ++ly) {
+            const int sy = reflect101(y0 - R + ly, H);
+            const int ph = span_phase(img + ((size_t)sy * W + cx0) * 3);
+            for (int i = tid; i < span; i += 256) s_row[ly][ph + i] = s_map[s_row[ly][ph + i]];
+        }
+        __syncthreads();
+    }
+    if (enhanced) {
+        const int ix0 = x0, ix1 = min(x0 + FW, W);
+        for (int ly = R; ly < GH - R; ++ly) {
+            const int Y = y0 - R + ly;
+            if (Y >= H) break;
+            // same row of the same frame layout => same phase for source and destination
+            // only when src and dst bases agree modulo 16; handle generally via a byte loop otherwise
+            const uint8_t *srow = img + ((size_t)Y * W + cx0) * 3;
+            uint8_t *drow = enhanced + fo * 3 + ((size_t)Y * W + ix0) * 3;
+            const int ph = span_phase(srow);
+            const uint8_t *sp = s_row[ly] + ph + (ix0 - cx0) * 3;
+            const int nb = (ix1 - ix0) * 3;
+            if (((reinterpret_cast<uintptr_t>(sp) ^ reinterpret_cast<uintptr_t>(drow)) & 15) == 0) {
+                // aligned-compatible: reuse the span copier with the implied base
+                s2g_span(drow, sp - span_phase(drow), nb, tid, 256);
+            } else {
+                for (int i = tid; i < nb; i += 256) drow[i] = sp[i];
+            }
+        }
+    }
+    // gray of every staged position (mirror columns map into the staged span)
+    for (int i = tid; i < GH * GW; i += 256) {
+        const int ly = i / GW, lx = i - ly * GW;
+        if (x0 - R + lx >= W + R) continue;   // beyond any mirrored column a valid output can need
+        const int sy = reflect101(y0 - R + ly, H);
+        const int sx = reflect101(x0 - R + lx, W);
+        const int ph = span_phase(img + ((size_t)sy * W + cx0) * 3);
+        const uint8_t *p = s_row[ly] + ph + (sx - cx0) * 3;
+        const int gv = gray_px(p[0], p[1], p[2]);
+        s_g[ly][lx] = (uint8_t)gv;
+    }
+    __syncthreads();
+    if (gray) {
+        for (int i = tid; i < FH * (FW / 4); i += 256) {
+            const int ly = i / (FW / 4), lx = (i - ly * (FW / 4)) * 4;
+            const int Y = y0 + ly, X = x0 + lx;
+            if (Y >= H || X >= W) continue;
+            uint8_t *o = gray + fo + (size_t)Y * W + X;
+            const uint8_t *s = &s_g[ly + R][lx + R];
+            if (X + 3 < W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(o) = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+            } else {
+                for (int j = 0; j < 4 && X + j < W; ++j) o[j] = s[j];
+            }
+        }
+    }
+    // blur 5x5: [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8
+    for (int i = tid; i < GH * FW; i += 256) {
+        const int ly = i / FW, lx = i - ly * FW;
+        const uint8_t *s = &s_g[ly][lx];
+        s_h[ly][lx] = (uint16_t)(s[0] + 4 * s[1] + 6 * s[2] + 4 * s[3] + s[4]);
+    }
+    __syncthreads();
+    int *myh = s_hist[tid >> 5];
+    for (int i = tid; i < FH * (FW / 4); i += 256) {
+        const int ly = i / (FW / 4), lx = (i - ly * (FW / 4)) * 4;
+        const int Y = y0 + ly, X = x0 + lx;
+        if (Y >= H || X >= W) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = (s_h[ly][lx + j] + 4 * s_h[ly + 1][lx + j] + 6 * s_h[ly + 2][lx + j] + 4 * s_h[ly + 3][lx + j] +
+                           s_h[ly + 4][lx + j] + 128) >> 8;
+            if (X + j < W) {
+                packed |= (uint32_t)v << (8 * j);
+                if (hist) atomicAdd(&myh[v], 1);
+            }
+        }
+        if (blurred) {
+            uint8_t *o = blurred + fo + (size_t)Y * W + X;
+            if (X + 3 < W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t *>(o) = packed;
+            else
+                for (int j = 0; j < 4 && X + j < W; ++j) o[j] = (uint8_t)(packed >> (8 * j));
+        }
+    }
+    if (hist) {
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_hist[w][tid];
+        if (tot) atomicAdd(&hist[(size_t)frame * 256 + tid], tot);
+    }
+}
+int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const int32_t *minmax, uint8_t *enhanced,
+                  uint8_t *gray, uint8_t *blurred, int32_t *hist)
+{
+    if (hist) CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * (size_t)n, h->stream));
+    dim3 grid((W + 127) / 128, (H + 15) / 16, n);
+    if (minmax) k_finish<true><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
+    else k_finish<false><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// S9: Otsu threshold, OpenCV's f64 loop verbatim in structure (thresh.cpp
+// getThreshVal_Otsu_8u): sequential recurrences, strict '>' so the first
+// maximum wins.  One warp per frame; lane 0 walks the 256 bins.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_otsu(const int32_t *__restrict__ hist, long npx, int32_t *__restrict__ otsu_t)
+{
+    __shared__ double s_p[256];
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const int32_t *hh = hist + (size_t)frame * 256;
+    const double scale = __ddiv_rn(1.0, (double)npx);
+    for (int i = lane; i < 256; i += 32) s_p[i] = __dmul_rn((double)hh[i], scale);
+    __syncwarp();
+    if (lane == 0) {
+        double mu = 0;
+        for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)hh[i]));
+        mu = __dmul_rn(mu, scale);
+        double mu1 = 0, q1 = 0, max_sigma = 0;
+        int max_val = 0;
+        for (int i = 0; i < 256; ++i) {
+            const double p_i = s_p[i];
+            mu1 = __dmul_rn(mu1, q1);
+            q1 = __dadd_rn(q1, p_i);
+            const double q2 = __dsub_rn(1.0, q1);
+            if (fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON) continue;
+            mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+            const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+            const double d = __dsub_rn(mu1, mu2);
+            const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+            if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+        }
+        otsu_t[frame] = max_val;
+    }
+}
+int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t)
+{
+    k_otsu<<<n, 32, 0, h->stream>>>(hist, npx, otsu_t);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// Pass 4: binary mask, 16 pixels per thread per step
+__global__ void __launch_bounds__(256) k_threshold(const uint8_t *__restrict__ src, long npx,
+                                                   const int32_t *__restrict__ otsu_t, uint8_t *__restrict__ dst)
+{
+    const int frame = blockIdx.y;
+    const uint32_t T = (uint32_t)otsu_t[frame];
+    const uint8_t *p = src + (size_t)frame * npx;
+    uint8_t *o = dst + (size_t)frame * npx;
+    const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+    const long nvec = al ? npx / 16 : 0;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+        uint32_t *w = &q.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = w[k];
+            w[k] = ((v & 0xff) > T ? 0xffu : 0u) | (((v >> 8) & 0xff) > T ? 0xff00u : 0u) |
+                   (((v >> 16) & 0xff) > T ? 0xff0000u : 0u) | ((v >> 24) > T ? 0xff000000u : 0u);
+        }
+        reinterpret_cast<uint4 *>(o)[i] = q;
+    }
+    for (long i = nvec * 16 + (long)blockIdx.x * 256 + threadIdx.x; i < npx; i += (long)gridDim.x * 256)
+        o[i] = p[i] > T ? 255 : 0;
+}
+int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const int32_t *otsu_t, uint8_t *dst)
+{
+    int bx = stream_blocks(npx / 16, 16 * h->sm_count / (n > 0 ? n : 1));
+    dim3 grid(bx, n);
+    k_threshold<<<grid, 256, 0, h->stream>>>(src, npx, otsu_t, dst);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}

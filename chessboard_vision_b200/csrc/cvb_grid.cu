@@ -1,0 +1,291 @@
+// board_detection.warp_image, grid_extractor squares and the per-square
+// change_detector / piece_detector statistics as sm_100a kernels.
+//
+// Reference: board_detection.py:61-71 (warp), grid_extractor.py:33-56,140-161
+// (square rectangles), change_detector.py:36-167, piece_detector.py:82-97,
+// 124-207,305 (statistics).  Compiled with -fmad=false.
+#include "cvb_device.cuh"
+#include <cmath>
+
+static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the ABI");
+
+#define LAUNCH_CHECK(h)                                  \
+    do {                                                 \
+        (h)->launches++;                                 \
+        CVB_CHECK_CUDA(cudaGetLastError());              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// cv2.warpPerspective, INTER_LINEAR, BORDER_CONSTANT(0)  (imgwarp.cpp
+// WarpPerspectiveInvoker + remapBilinear): destination -> source coordinates in
+// f64 with the invoker's 64-column block association, fixed point with 5
+// fractional bits, weights (32-ax)(32-ay).., (sum + 512) >> 10.
+// One thread per destination pixel.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, int H, int W,
+                                              const double *__restrict__ minv, int n_mats, int OH, int OW,
+                                              uint8_t *__restrict__ dst)
+{
+    const int frame = blockIdx.z;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= OW || y >= OH) return;
+    const double *M = minv + (n_mats == 1 ? 0 : (size_t)frame * 9);
+    const double bx = (double)(x & ~63), x1 = (double)(x & 63), yy = (double)y;
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
+    double Wd = __dadd_rn(W0, __dmul_rn(M[6], x1));
+    Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
+    double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], x1)), Wd);
+    double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], x1)), Wd);
+    fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+    fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int ax = X & 31, ay = Y & 31;
+    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+    const uint8_t *img = src + (size_t)frame * H * W * 3;
+    const bool x0in = sx >= 0 && sx < W, x1in = sx + 1 >= 0 && sx + 1 < W;
+    const bool y0in = sy >= 0 && sy < H, y1in = sy + 1 >= 0 && sy + 1 < H;
+    int acc[3] = {0, 0, 0};
+    if (y0in) {
+        const uint8_t *r = img + (size_t)sy * W * 3;
+        if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
+        if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w01 * p[0]; acc[1] += w01 * p[1]; acc[2] += w01 * p[2]; }
+    }
+    if (y1in) {
+        const uint8_t *r = img + (size_t)(sy + 1) * W * 3;
+        if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w10 * p[0]; acc[1] += w10 * p[1]; acc[2] += w10 * p[2]; }
+        if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w11 * p[0]; acc[1] += w11 * p[1]; acc[2] += w11 * p[2]; }
+    }
+    uint8_t *o = dst + ((size_t)frame * OH * OW + (size_t)y * OW + x) * 3;
+    o[0] = (uint8_t)((acc[0] + 512) >> 10);
+    o[1] = (uint8_t)((acc[1] + 512) >> 10);
+    o[2] = (uint8_t)((acc[2] + 512) >> 10);
+}
+int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats, int out_h,
+                int out_w, uint8_t *warped)
+{
+    dim3 grid((out_w + 63) / 64, (out_h + 3) / 4, n);
+    k_warp<<<grid, 256, 0, h->stream>>>(bgr, H, W, d_minv, n_mats, out_h, out_w, warped);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-square kernel: one block per (square, frame).
+//   gray (S7) -> Gaussian k (S8, borders reflected inside the square, as the
+//   reference blurs each square view on its own) -> fused reductions:
+//     PieceDetector: sum, sum^2, SAD vs reference, centre/corner/ring sums
+//     ChangeDetector: f32 z-score count/max, EMA update of mean/variance
+// ---------------------------------------------------------------------------------------
+struct SquareArgs {
+    const uint8_t *boards;
+    int BH, BW, C;
+    const cvb_rect *rects;
+    const int32_t *mask_ofs;
+    const uint8_t *masks;
+    const uint8_t *select;
+    uint8_t *pd_ref, *pd_cur, *flags;
+    float *cd_mean, *cd_var;
+    int stream0;
+    cvb_square_params p;
+    int pd_q[31], cd_q[31];
+    cvb_square_stats *stats;
+};
+
+CVB_DEV int blur_at(const uint16_t *s_h, const int *q, int k, int x, int y, int w, int h)
+{
+    const int r = k >> 1;
+    uint32_t s = 0;
+    for (int i = 0; i < k; ++i) s += (uint32_t)q[i] * s_h[reflect101(y + i - r, h) * w + x];
+    return (int)((s + 32768u) >> 16);
+}
+CVB_DEV void hpass(const uint8_t *s_g, uint16_t *s_h, const int *q, int k, int w, int h, int tid)
+{
+    const int r = k >> 1;
+    for (int i = tid; i < w * h; i += 256) {
+        const int y = i / w, x = i - y * w;
+        uint32_t s = 0;
+        for (int j = 0; j < k; ++j) s += (uint32_t)q[j] * s_g[y * w + reflect101(x + j - r, w)];
+        s_h[i] = (uint16_t)s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sq_smem[];
+    __shared__ unsigned long long s_acc[16];
+    __shared__ unsigned s_cd_nan;
+    __shared__ int s_cd_zbits;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sq = blockIdx.x, frame = blockIdx.y;
+    const cvb_rect rc = a.rects[sq];
+    const int w = rc.w, h = rc.h, n = w * h;
+    uint8_t *s_g = sq_smem;
+    uint16_t *s_h = reinterpret_cast<uint16_t *>(sq_smem + ((n + 15) & ~15));
+    const size_t plane = (size_t)a.BH * a.BW;
+    const size_t so = (size_t)(a.stream0 + frame) * plane;       // state slot offset
+    const uint8_t *board = a.boards + (size_t)frame * plane * a.C;
+    const bool selected = a.select ? a.select[sq] != 0 : true;
+    const int ops = a.p.ops;
+
+    if (tid < 16) s_acc[tid] = 0ull;
+    if (tid == 0) { s_cd_nan = 0; s_cd_zbits = __float_as_int(-INFINITY); }
+    for (int i = tid; i < n; i += 256) {
+        const int y = i / w, x = i - y * w;
+        const uint8_t *p = board + ((size_t)(rc.y + y) * a.BW + rc.x + x) * a.C;
+        s_g[i] = a.C == 3 ? (uint8_t)gray_px(p[0], p[1], p[2]) : p[0];
+    }
+    __syncthreads();
+
+    const size_t first = so + (size_t)rc.y * a.BW + rc.x;
+    const bool state = a.flags != nullptr;
+    const int fl0 = state ? a.flags[first] : 0;
+    const bool has_ref = (fl0 & 1) != 0;
+    bool has_cd = (fl0 & 2) != 0;
+
+    // ---- PieceDetector pass (blur pd_blur) ----
+    const bool need_pd = (ops & (CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF)) != 0;
+    const bool need_cd = (ops & (CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE)) != 0 && selected && state;
+    const bool same_blur = a.p.pd_blur == a.p.cd_blur;
+    if (need_pd || (need_cd && same_blur)) hpass(s_g, s_h, a.pd_q, a.p.pd_blur, w, h, tid);
+    __syncthreads();
+
+    unsigned sum = 0, sad = 0, csum = 0, ccnt = 0, bsum = 0, bcnt = 0;
+    unsigned rsum[4] = {0, 0, 0, 0}, rcnt[4] = {0, 0, 0, 0};
+    unsigned long long sumsq = 0;
+    unsigned cd_cnt = 0;
+    float cd_zmax = -INFINITY;
+    bool cd_nan = false;
+    const uint8_t *mask = a.masks + a.mask_ofs[sq];
+
+    auto cd_pixel = [&](int gv, size_t o) {
+        const float gf = (float)gv;
+        float m, v;
+        if (ops & CVB_SQ_CD_CALIBRATE) {
+            m = gf; v = a.p.initial_variance;
+            a.cd_mean[o] = m; a.cd_var[o] = v;
+            a.flags[o] |= 2;
+        } else {
+            if (!has_cd) return;
+            m = a.cd_mean[o]; v = a.cd_var[o];
+        }
+        if (ops & CVB_SQ_CD_DETECT) {
+            const float z = __fdiv_rn(fabsf(__fsub_rn(gf, m)), __fsqrt_rn(v));
+            if (z > a.p.z_threshold) ++cd_cnt;
+            if (z != z) cd_nan = true; else cd_zmax = fmaxf(cd_zmax, z);
+        }
+        if (ops & CVB_SQ_CD_UPDATE) {
+            // change_detector.py:82-89, every product and sum rounded on its own
+            const float nm = __fadd_rn(__fmul_rn(a.p.one_minus_alpha, m), __fmul_rn(a.p.alpha, gf));
+            const float d = __fsub_rn(gf, nm);
+            float nv = __fadd_rn(__fmul_rn(a.p.one_minus_alpha, v), __fmul_rn(a.p.alpha, __fmul_rn(d, d)));
+            if (!(nv > a.p.min_variance) && nv == nv) nv = a.p.min_variance;   // np.maximum keeps NaN
+            a.cd_mean[o] = nm; a.cd_var[o] = nv;
+        }
+    };
+
+    if (need_pd || (need_cd && same_blur)) {
+        for (int i = tid; i < n; i += 256) {
+            const int y = i / w, x = i - y * w;
+            const int gv = blur_at(s_h, a.pd_q, a.p.pd_blur, x, y, w, h);
+            const size_t o = so + (size_t)(rc.y + y) * a.BW + rc.x + x;
+            if (ops & CVB_SQ_PD_STATS) {
+                const int m = mask[i];
+                sum += gv; sumsq += (unsigned)(gv * gv);
+                if (has_ref) sad += (unsigned)abs(gv - (int)a.pd_ref[o]);
+                if (m & 1) { csum += gv; ++ccnt; }
+                if (m & 2) { bsum += gv; ++bcnt; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (m & (4 << k)) { rsum[k] += gv; ++rcnt[k]; }
+            }
+            if (state && need_pd) a.pd_cur[o] = (uint8_t)gv;
+            if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { a.pd_ref[o] = (uint8_t)gv; a.flags[o] |= 1; }
+            if (need_cd && same_blur) cd_pixel(gv, o);
+        }
+    }
+    // ---- ChangeDetector pass when its blur differs ----
+    if (need_cd && !same_blur) {
+        __syncthreads();
+        hpass(s_g, s_h, a.cd_q, a.p.cd_blur, w, h, tid);
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) {
+            const int y = i / w, x = i - y * w;
+            const int gv = blur_at(s_h, a.cd_q, a.p.cd_blur, x, y, w, h);
+            cd_pixel(gv, so + (size_t)(rc.y + y) * a.BW + rc.x + x);
+        }
+    }
+    if (!a.stats) return;
+
+    // ---- block reduction ----
+    unsigned long long vals[16] = {sum, sumsq, sad, csum, ccnt, bsum, bcnt, rsum[0], rsum[1], rsum[2], rsum[3],
+                                   rcnt[0], rcnt[1], rcnt[2], rcnt[3], cd_cnt};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned long long r = warp_sum_ull(vals[k]);
+        if (lane == 0 && r) atomicAdd(&s_acc[k], r);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cd_zmax = fmaxf(cd_zmax, __shfl_xor_sync(0xffffffffu, cd_zmax, o));
+    const unsigned any_nan = __ballot_sync(0xffffffffu, cd_nan);
+    if (lane == 0) {
+        // non-NaN z is >= +0, so its bit pattern orders like a signed int; -inf (no pixel) is negative
+        atomicMax(&s_cd_zbits, __float_as_int(cd_zmax));
+        if (any_nan) atomicOr(&s_cd_nan, 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cvb_square_stats st;
+        memset(&st, 0, sizeof st);
+        st.n = n;
+        st.has_ref = has_ref ? 1 : 0;
+        st.sum = (uint32_t)s_acc[0]; st.sumsq = s_acc[1]; st.sad = (uint32_t)s_acc[2];
+        st.center_sum = (uint32_t)s_acc[3]; st.center_cnt = (uint32_t)s_acc[4];
+        st.border_sum = (uint32_t)s_acc[5]; st.border_cnt = (uint32_t)s_acc[6];
+        for (int k = 0; k < 4; ++k) { st.ring_sum[k] = (uint32_t)s_acc[7 + k]; st.ring_cnt[k] = (uint32_t)s_acc[11 + k]; }
+        const bool cd_ran = need_cd && (ops & CVB_SQ_CD_DETECT) && (has_cd || (ops & CVB_SQ_CD_CALIBRATE));
+        st.cd_valid = cd_ran ? 1 : 0;
+        st.cd_changed = (int32_t)s_acc[15];
+        st.cd_zmax = s_cd_nan ? __int_as_float(0x7fc00000) : __int_as_float(s_cd_zbits);   // np.max propagates NaN
+        a.stats[(size_t)frame * gridDim.x + sq] = st;
+    }
+}
+
+int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C, const cvb_rect *d_rects,
+                   const int32_t *d_mask_ofs, const uint8_t *d_masks, int n_sq, int max_px, const uint8_t *d_select,
+                   cvb_state *st, int stream0, const cvb_square_params &p, const int *pd_q, const int *cd_q,
+                   cvb_square_stats *stats)
+{
+    SquareArgs a;
+    memset(&a, 0, sizeof a);
+    a.boards = boards; a.BH = BH; a.BW = BW; a.C = C; a.rects = d_rects; a.mask_ofs = d_mask_ofs; a.masks = d_masks;
+    a.select = d_select; a.stream0 = stream0; a.p = p; a.stats = stats;
+    if (st) { a.pd_ref = st->pd_ref; a.pd_cur = st->pd_cur; a.flags = st->flags; a.cd_mean = st->cd_mean; a.cd_var = st->cd_var; }
+    memcpy(a.pd_q, pd_q, sizeof a.pd_q);
+    memcpy(a.cd_q, cd_q, sizeof a.cd_q);
+    const size_t smem = (((size_t)max_px + 15) & ~(size_t)15) + (size_t)max_px * 2;
+    if (smem > 200 * 1024) {
+        cvb_set_error("square of %d pixels needs %zu bytes of shared memory (max 204800)", max_px, smem);
+        return CVB_ERR_INVALID;
+    }
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+        CVB_CHECK_CUDA(cudaFuncSetAttribute(k_squares, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
+    }
+    dim3 grid(n_sq, n);
+    k_squares<<<grid, 256, smem, h->stream>>>(a);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+int launch_state_reset(cvb_handle *h, cvb_state *s, int stream)
+{
+    const size_t plane = (size_t)s->BH * s->BW;
+    uint8_t *p = s->flags + (stream < 0 ? 0 : (size_t)stream * plane);
+    const size_t n = stream < 0 ? plane * s->n_streams : plane;
+    CVB_CHECK_CUDA(cudaMemsetAsync(p, 0, n, h->stream));
+    return CVB_OK;
+}

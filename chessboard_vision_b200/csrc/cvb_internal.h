@@ -1,0 +1,122 @@
+// Internal declarations shared by the translation units of libcvb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/cvb200.h"
+
+// ---- error plumbing ---------------------------------------------------------
+void cvb_set_error(const char *fmt, ...);
+#define CVB_CHECK_CUDA(expr)                                                           \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            cvb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),     \
+                          __FILE__, __LINE__);                                         \
+            return CVB_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+#define CVB_REQUIRE(cond, ...)                                                         \
+    do {                                                                               \
+        if (!(cond)) { cvb_set_error(__VA_ARGS__); return CVB_ERR_INVALID; }           \
+    } while (0)
+#define CVB_TRY(expr)                                                                  \
+    do { int _rc = (expr); if (_rc != CVB_OK) return _rc; } while (0)
+
+// ---- tables -----------------------------------------------------------------
+// Integer colour-conversion LUTs (restating OpenCV color_lab.cpp, see
+// cvb_tables.cpp) in the layout the kernels stage into shared memory.
+struct CvbTables {
+    uint16_t gamma[256];       // sRGBGammaTab_b
+    uint16_t cbrt[2048];       // LabCbrtTab_b, index <= 2040 reachable
+    int32_t  lab2yf[512];      // LabToYF_b (y, ify)
+    uint8_t  invgamma[4096];   // sRGBInvGammaTab_b
+    uint8_t  ltab[2048];       // L as a function of the Y index (histogram pass)
+};
+const CvbTables &cvb_host_tables();
+void cvb_host_bilateral_tables(double sigma_color, double sigma_space, float *color768, float *space81);
+int  cvb_host_gaussian_q8(int ksize, int *q);
+int  cvb_host_get_perspective(const float *src, const float *dst, double *M);
+int  cvb_host_invert3(const double *a, double *t);
+void cvb_host_square_masks(int h, int w, uint8_t *mask);
+
+// ---- device workspace -----------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct cvb_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    int64_t launches = 0;
+    CvbTables *d_tables = nullptr;
+    // bilateral colour LUT cache (device) keyed by sigma_color
+    float *d_color = nullptr;
+    double color_sigma = -1.0;
+    // grow-only scratch
+    DevBuf ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
+    DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_stats, ws_rects, ws_select, ws_mats;
+    // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
+    DevBuf ws_masks;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+struct cvb_state {
+    cvb_handle *h = nullptr;
+    int n_streams = 0, BH = 0, BW = 0;
+    uint8_t *pd_ref = nullptr;   // n_streams * BH*BW
+    uint8_t *pd_cur = nullptr;
+    float *cd_mean = nullptr;
+    float *cd_var = nullptr;
+    uint8_t *flags = nullptr;    // per pixel: bit0 has_ref, bit1 has_cd
+};
+
+int cvb_ws(cvb_handle *h, DevBuf &b, size_t bytes, void **out);
+
+// ---- kernel launchers (cvb_enhance.cu) --------------------------------------------
+struct ClaheGeom {
+    int tiles_x, tiles_y, tile_w, tile_h, ext_w, ext_h, clip;
+    float lut_scale, inv_tw, inv_th;
+};
+int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g);
+
+int launch_bgr2lab(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *lab);
+int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr);
+// histogram of L (from_bgr=1: src is BGR, L computed on the fly) or of a u8 plane
+int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W,
+                     const ClaheGeom &g, int32_t *hist, int32_t *minmax_init);
+int launch_clahe_lut(cvb_handle *h, const int32_t *hist, int n, const ClaheGeom &g, uint8_t *lut);
+int launch_clahe_apply_plane(cvb_handle *h, const uint8_t *src, int n, int H, int W, const ClaheGeom &g,
+                             const uint8_t *lut, uint8_t *dst);
+int launch_correct_lighting(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const ClaheGeom &g,
+                            const uint8_t *lut, uint8_t *out);
+// the fused tile kernel: [lighting] -> [bilateral] -> [sharpen] (+ min/max)
+int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool light, bool bilateral, bool sharpen,
+                 const ClaheGeom *g, const uint8_t *lut, double sigma_color, double sigma_space,
+                 uint8_t *out, int32_t *minmax);
+int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, int32_t *minmax);
+int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, const int32_t *minmax,
+                     uint8_t *out);
+int launch_gray(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *gray);
+int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, uint8_t *dst);
+// normalize (optional) + gray + blur5 + 256-bin histogram
+int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const int32_t *minmax,
+                  uint8_t *enhanced, uint8_t *gray, uint8_t *blurred, int32_t *hist);
+int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t);
+int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const int32_t *otsu_t, uint8_t *dst);
+
+// ---- cvb_grid.cu ----------------------------------------------------------------------
+int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats,
+                int out_h, int out_w, uint8_t *warped);
+int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C,
+                   const cvb_rect *d_rects, const int32_t *d_mask_ofs, const uint8_t *d_masks, int n_sq, int max_px,
+                   const uint8_t *d_select, cvb_state *st, int stream0, const cvb_square_params &p,
+                   const int *pd_q, const int *cd_q, cvb_square_stats *stats);
+int launch_state_reset(cvb_handle *h, cvb_state *s, int stream);

@@ -1,0 +1,249 @@
+/*
+ * cvb200.h -- C ABI of libcvb200.so: the B200-native (sm_100a) implementation
+ * of the ChessVision per-frame hot path (hericmr/chessboard-vision).
+ *
+ * The reference has no FFI of its own: its "native" seam is the module-level
+ * selector `from src.cython.<mod> import <Class>` (frame_enhancer.py:8-21,
+ * 184-189; change_detector.py:7-19,203-208; setup.py:5-18).  The entry points
+ * below are what a ctypes binding placed at that seam calls; each one cites
+ * the reference method whose arithmetic it replaces.  INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / numpy types.
+ *  - every function returns 0 on success, a negative cvb_status otherwise;
+ *    cvb_last_error() returns a thread-local message for the last failure.
+ *  - images: uint8, interleaved HxWxC, rows contiguous, frames of a batch
+ *    contiguous (frame stride = H*W*C).  `n` is the batch size.
+ *  - *_dev functions take DEVICE pointers and only enqueue work on the
+ *    handle's stream (call cvb_synchronize or order your own stream after
+ *    it).  Functions without the suffix take HOST pointers, copy in/out and
+ *    return after the results are in the host buffers.
+ *  - there is no CPU fallback: without a CUDA device cvb_create fails.
+ *  - a handle is single-threaded (one handle per thread / GPU).
+ */
+#ifndef CVB200_H
+#define CVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built -fvisibility=hidden */
+#endif
+
+#define CVB_VERSION 100
+
+typedef struct cvb_handle cvb_handle;
+
+typedef enum {
+    CVB_OK = 0,
+    CVB_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+    CVB_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail)  */
+    CVB_ERR_NO_DEVICE = -3,   /* no usable sm_100 device                      */
+    CVB_ERR_STATE = -4        /* per-stream state missing / shape mismatch    */
+} cvb_status;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int  cvb_version(void);
+int  cvb_device_count(void);
+const char *cvb_last_error(void);
+int  cvb_create(int device, cvb_handle **out);
+void cvb_destroy(cvb_handle *h);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL
+ * restores the handle's own stream */
+int  cvb_set_stream(cvb_handle *h, void *cuda_stream);
+int  cvb_synchronize(cvb_handle *h);
+/* number of kernels this handle has launched since creation (bench.py's
+ * gpu_launches claim is read from here) */
+int64_t cvb_launch_count(cvb_handle *h);
+
+/* ---- device / pinned memory helpers (so hosts need no torch) --------------- */
+int cvb_malloc(cvb_handle *h, size_t bytes, void **dptr);
+int cvb_free(cvb_handle *h, void *dptr);
+int cvb_host_alloc(size_t bytes, void **hptr);            /* pinned */
+int cvb_host_free(void *hptr);
+int cvb_memcpy_h2d(cvb_handle *h, void *dst, const void *src, size_t bytes);  /* async on stream */
+int cvb_memcpy_d2h(cvb_handle *h, void *dst, const void *src, size_t bytes);  /* async on stream */
+int cvb_memset(cvb_handle *h, void *dst, int value, size_t bytes);
+/* CUDA-event timers on the handle's stream */
+int cvb_event_create(void **ev);
+int cvb_event_destroy(void *ev);
+int cvb_event_record(cvb_handle *h, void *ev);
+int cvb_event_elapsed_ms(void *start, void *stop, float *ms);   /* syncs on stop */
+
+/* ---- parameters -------------------------------------------------------------- */
+typedef struct {
+    double clahe_clip_limit;   /* frame_enhancer.py:28  default 3.0            */
+    int    tiles_x, tiles_y;   /* tileGridSize           default 8,8 (<=16)    */
+    int    bilateral_d;        /* frame_enhancer.py:131  must be 9             */
+    double sigma_color;        /*                         75                    */
+    double sigma_space;        /*                         75                    */
+} cvb_enhance_params;
+void cvb_enhance_params_default(cvb_enhance_params *p);
+
+/* host-side table access (no GPU needed): the integer / f32 LUTs the kernels
+ * use, for inspection and CPU-side tests.  Any pointer may be NULL. */
+int cvb_get_tables(uint16_t *gamma256, uint16_t *cbrt2048, int32_t *lab2yf512,
+                   uint8_t *invgamma4096, uint8_t *ltab2048);
+int cvb_get_bilateral_tables(double sigma_color, double sigma_space,
+                             float *color768, float *space81 /* [dy+4][dx+4], 0 outside r<=4 */);
+int cvb_gaussian_kernel_q8(int ksize, int *q /* ksize entries */);
+
+/* ---- frame_enhancer stages (stage-isolated entry points) -------------------- */
+/* S1 cv2.cvtColor(BGR2LAB)                       frame_enhancer.py:108 */
+int cvb_bgr2lab_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *lab);
+/* S3 cv2.cvtColor(LAB2BGR)                       frame_enhancer.py:120 */
+int cvb_lab2bgr_dev(cvb_handle *h, const uint8_t *lab, int n, int H, int W, uint8_t *bgr);
+/* S2 clahe.apply on one u8 plane                 frame_enhancer.py:36,114
+ * hist_out: n*tiles*256 int32 or NULL; lut_out: n*tiles*256 u8 or NULL      */
+int cvb_clahe_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
+                  double clip_limit, int tiles_x, int tiles_y,
+                  uint8_t *out, int32_t *hist_out, uint8_t *lut_out);
+/* correct_lighting = S1+S2+S3 fused               frame_enhancer.py:101-120 */
+int cvb_correct_lighting_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                             double clip_limit, int tiles_x, int tiles_y,
+                             uint8_t *out, int32_t *hist_out, uint8_t *lut_out);
+/* S4 cv2.bilateralFilter(d=9, sigma, sigma)       frame_enhancer.py:122-131 */
+int cvb_bilateral_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                      int d, double sigma_color, double sigma_space, uint8_t *out);
+/* S5 cv2.filter2D 3x3 sharpen, 3 channels         frame_enhancer.py:133-138 */
+int cvb_sharpen_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *out);
+/* S6 cv2.normalize(NORM_MINMAX, 0, 255); C = channels (any)
+ * minmax_out: n*2 int32 DEVICE or NULL            frame_enhancer.py:140-146 */
+int cvb_normalize_dev(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C,
+                      uint8_t *out, int32_t *minmax_out);
+/* S7 cv2.cvtColor(BGR2GRAY)                       frame_enhancer.py:154 */
+int cvb_gray_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *gray);
+/* S8 cv2.GaussianBlur((k,k),0) on a u8 plane, k odd <= 31
+ *                                                frame_enhancer.py:156 */
+int cvb_gaussian_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, int ksize, uint8_t *out);
+/* prepare_analysis = S7+S8(5)+S9                  frame_enhancer.py:148-159
+ * blurred (n*H*W) / otsu_t (n int32, DEVICE) / hist (n*256 int32) may be NULL */
+int cvb_prepare_analysis_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                             uint8_t *gray, uint8_t *binary, uint8_t *blurred,
+                             int32_t *otsu_t, int32_t *hist);
+/* process_pipeline (colour profile off) = S1..S6    frame_enhancer.py:161-181 */
+int cvb_process_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                             const cvb_enhance_params *p, uint8_t *enhanced);
+/* process_pipeline + prepare_analysis in four passes;
+ * gray / binary / otsu_t (DEVICE int32[n]) may be NULL to skip the tail     */
+int cvb_enhance_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                    const cvb_enhance_params *p,
+                    uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t);
+/* host-buffer variant: H2D, cvb_enhance_dev, D2H, synchronise.  otsu_t: HOST
+ * int32[n].  Any output may be NULL.                                         */
+int cvb_enhance(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                const cvb_enhance_params *p,
+                uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t);
+
+/* ---- board_detection.warp_image ---------------------------------------------- */
+/* cv2.getPerspectiveTransform (host, f64 LU)       board_detection.py:65-68 */
+int cvb_get_perspective_transform(const float *src_xy4, const float *dst_xy4, double *M9);
+/* cv2.warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0); M9: HOST, n_mats * 9
+ * forward matrices (n_mats == 1: shared by the batch, else == n)
+ *                                                board_detection.py:69 */
+int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                 const double *M9, int n_mats, int out_h, int out_w, uint8_t *warped);
+
+/* ---- per-square statistics ------------------------------------------------------ */
+/* A "board" is an image (warped board or an atlas of packed squares) of
+ * BH x BW x C (C = 1 or 3); squares are rectangles inside it
+ * (grid_extractor.py:33-56,140-161).                                          */
+typedef struct { int32_t x, y, w, h; } cvb_rect;
+
+/* per (frame, square) result; layout is part of the ABI (128 bytes)          */
+typedef struct {
+    int32_t  n;                 /* pixels in the square                         */
+    int32_t  has_ref;           /* 1 when a PD reference existed                */
+    uint32_t sum;               /* sum g        (g = gray+blur5 square)         */
+    uint32_t sad;               /* sum |g-ref|  piece_detector.py:87-93         */
+    uint64_t sumsq;             /* sum g^2      piece_detector.py:305           */
+    uint32_t center_sum, center_cnt;      /* piece_detector.py:184-201          */
+    uint32_t border_sum, border_cnt;
+    uint32_t ring_sum[4], ring_cnt[4];    /* piece_detector.py:148-166          */
+    int32_t  cd_changed;        /* #(z > z_threshold) change_detector.py:129-131 */
+    float    cd_zmax;           /* max z                change_detector.py:159  */
+    int32_t  cd_valid;          /* 1 when CD state existed and square selected  */
+    int32_t  reserved[11];
+} cvb_square_stats;
+
+/* per-stream state (ChangeDetector means/variances, PieceDetector reference):
+ * planes of BH x BW living on the device, one set per stream slot            */
+typedef struct cvb_state cvb_state;
+int  cvb_state_create(cvb_handle *h, int n_streams, int BH, int BW, cvb_state **out);
+void cvb_state_destroy(cvb_state *s);
+
+enum {
+    CVB_SQ_PD_STATS     = 1,    /* moments, centre/border, rings, SAD vs ref    */
+    CVB_SQ_PD_SET_REF   = 2,    /* ref <- g for selected squares (after stats)  */
+    CVB_SQ_CD_CALIBRATE = 4,    /* mean <- g, var <- initial_variance           */
+    CVB_SQ_CD_DETECT    = 8,    /* z-score count / max                          */
+    CVB_SQ_CD_UPDATE    = 16    /* EMA update (after detect)                    */
+};
+typedef struct {
+    int   ops;                  /* bitmask above                                */
+    int   pd_blur;              /* PieceDetector blur, 5   piece_detector.py:133 */
+    int   cd_blur;              /* ChangeDetector blur_kernel|1  change_detector.py:55 */
+    float z_threshold;          /* 2.5                                          */
+    float alpha;                /* f32(alpha)                                   */
+    float one_minus_alpha;      /* f32(1-alpha)                                 */
+    float initial_variance;     /* 100                                          */
+    float min_variance;         /* 10   change_detector.py:89                   */
+} cvb_square_params;
+void cvb_square_params_default(cvb_square_params *p);
+
+/* boards: n x BH x BW x C (DEVICE).  rects: HOST, n_sq entries (shared by the
+ * batch).  select: HOST n_sq bytes or NULL (all) -- squares with select==0 are
+ * skipped for the state-changing / CD ops (focus_squares).  Frame i uses
+ * state slot stream0+i.  stats: DEVICE n*n_sq cvb_square_stats or NULL.      */
+int cvb_squares_dev(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C,
+                    const cvb_rect *rects, int n_sq, const uint8_t *select,
+                    cvb_state *state, int stream0, const cvb_square_params *p,
+                    cvb_square_stats *stats);
+/* state <-> host; plane: 0 pd_ref(u8) 1 cd_mean(f32) 2 cd_var(f32)
+ * 3 pd_cur(u8: last gray+blur of pd_blur) 4 flags(u8 per pixel: bit0 has_ref,
+ * bit1 has_cd).  Buffers are BH*BW elements.                                 */
+int cvb_state_get(cvb_handle *h, cvb_state *s, int stream, int plane, void *host_out);
+int cvb_state_set(cvb_handle *h, cvb_state *s, int stream, int plane, const void *host_in);
+/* forget PD references / CD model of one stream slot (-1: all)               */
+int cvb_state_reset(cvb_handle *h, cvb_state *s, int stream);
+
+/* ---- the whole hot path for a batch ------------------------------------------------ */
+typedef struct {
+    cvb_enhance_params enhance;
+    cvb_square_params  squares;
+    int warp_enhanced;          /* 1: warp the enhanced frame, 0: the raw frame  */
+    int board_size;             /* 620 = min(1280,720)-100  board_detection.py:65 */
+} cvb_pipeline_params;
+void cvb_pipeline_params_default(cvb_pipeline_params *p);
+
+/* enhance -> prepare_analysis -> warp -> 64 squares -> PD/CD statistics.
+ * All pointers DEVICE except M9 / rects / select (HOST).  enhanced, gray,
+ * binary, warped may be NULL: the library then uses its own workspace.       */
+int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                     const cvb_pipeline_params *p,
+                     const double *M9, int n_mats,
+                     const cvb_rect *rects, int n_sq, const uint8_t *select,
+                     cvb_state *state, int stream0,
+                     uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t,
+                     uint8_t *warped, cvb_square_stats *stats);
+/* host-buffer variant (the call the Python shim times as "e2e"): bgr HOST
+ * (pinned or pageable) in; stats / otsu_t HOST out.                           */
+int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                 const cvb_pipeline_params *p,
+                 const double *M9, int n_mats,
+                 const cvb_rect *rects, int n_sq, const uint8_t *select,
+                 cvb_state *state, int stream0,
+                 int32_t *otsu_t, cvb_square_stats *stats);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVB200_H */

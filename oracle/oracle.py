@@ -1,0 +1,280 @@
+"""ctypes front-end of oracle/cvb_oracle.c (CPU oracle, test infrastructure).
+
+Every function mirrors one stage of the reference hot path; the reference
+file:line each stands in for is cited in cvb_oracle.c.  Parity pinning: see
+tests/test_oracle_golden.py (golden vectors produced by the unmodified
+reference, tools/make_golden.py) and tests/test_oracle_vs_cv2.py (live
+cv2, when importable).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcvb_oracle.so")
+
+
+def build(force=False):
+    """Compile the C restatement (gcc, seconds)."""
+    src = os.path.join(_HERE, "cvb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_otsu_from_hist.restype = C.c_int
+        _lib.orc_prepare_analysis.restype = C.c_int
+        _lib.orc_bilateral_tables.restype = C.c_int
+        _lib.orc_gaussian.restype = C.c_int
+        _lib.orc_gaussian_kernel_q8.restype = C.c_int
+        _lib.orc_get_perspective.restype = C.c_int
+        _lib.orc_invert3.restype = C.c_int
+        _lib.orc_square_preprocess.restype = C.c_int
+        _lib.orc_tables_init()
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == np.uint8
+    return a
+
+
+# --- tables -----------------------------------------------------------------
+def tables():
+    g = np.empty(256, np.uint16); c = np.empty(3072, np.uint16)
+    y = np.empty(512, np.int32); ig = np.empty(4096, np.uint8)
+    lib().orc_get_tables(_p(g), _p(c), _p(y), _p(ig))
+    return {"gamma": g, "cbrt": c, "lab2yf": y, "invgamma": ig}
+
+
+def bilateral_tables(d=9, sigma_color=75.0, sigma_space=75.0):
+    color = np.empty(768, np.float32); space = np.empty(512, np.float32)
+    dy = np.empty(512, np.int32); dx = np.empty(512, np.int32)
+    k = lib().orc_bilateral_tables(C.c_int(d), C.c_double(sigma_color), C.c_double(sigma_space),
+                                   _p(color), _p(space), _p(dy), _p(dx))
+    return color, space[:k].copy(), dy[:k].copy(), dx[:k].copy()
+
+
+def gaussian_kernel_q8(k):
+    q = np.zeros(31, np.int32)
+    if lib().orc_gaussian_kernel_q8(C.c_int(k), _p(q)):
+        raise ValueError("bad gaussian k=%r" % (k,))
+    return q[:k].copy()
+
+
+# --- enhancer stages ---------------------------------------------------------
+def bgr2lab(bgr):
+    bgr = _u8(bgr); out = np.empty_like(bgr)
+    lib().orc_bgr2lab(_p(bgr), C.c_long(bgr.size // 3), _p(out))
+    return out
+
+
+def lab2bgr(lab):
+    lab = _u8(lab); out = np.empty_like(lab)
+    lib().orc_lab2bgr(_p(lab), C.c_long(lab.size // 3), _p(out))
+    return out
+
+
+def clahe_geometry(H, W, tiles=(8, 8)):
+    tw = C.c_int(); th = C.c_int(); ew = C.c_int(); eh = C.c_int()
+    lib().orc_clahe_geometry(C.c_int(H), C.c_int(W), C.c_int(tiles[0]), C.c_int(tiles[1]),
+                             C.byref(tw), C.byref(th), C.byref(ew), C.byref(eh))
+    return tw.value, th.value, ew.value, eh.value
+
+
+def clahe(l, clip_limit=3.0, tiles=(8, 8), return_tables=False):
+    """tiles = (tilesX, tilesY) like cv2.createCLAHE(tileGridSize)."""
+    l = _u8(l); H, W = l.shape
+    nt = tiles[0] * tiles[1]
+    out = np.empty_like(l)
+    hist = np.empty((nt, 256), np.int32); lut = np.empty((nt, 256), np.uint8)
+    lib().orc_clahe(_p(l), C.c_int(H), C.c_int(W), C.c_double(clip_limit), C.c_int(tiles[0]), C.c_int(tiles[1]),
+                    _p(out), _p(hist), _p(lut))
+    return (out, hist, lut) if return_tables else out
+
+
+def correct_lighting(bgr, clip_limit=3.0, tiles=(8, 8)):
+    bgr = _u8(bgr); H, W, _ = bgr.shape; out = np.empty_like(bgr)
+    lib().orc_correct_lighting(_p(bgr), C.c_int(H), C.c_int(W), C.c_double(clip_limit),
+                               C.c_int(tiles[0]), C.c_int(tiles[1]), _p(out))
+    return out
+
+
+def bilateral(bgr, d=9, sigma_color=75.0, sigma_space=75.0, use_fma=True):
+    bgr = _u8(bgr); H, W, _ = bgr.shape; out = np.empty_like(bgr)
+    lib().orc_bilateral(_p(bgr), C.c_int(H), C.c_int(W), C.c_int(d), C.c_double(sigma_color),
+                        C.c_double(sigma_space), C.c_int(int(use_fma)), _p(out))
+    return out
+
+
+def sharpen(img):
+    img = _u8(img); H, W = img.shape[:2]; ch = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    lib().orc_sharpen(_p(img), C.c_int(H), C.c_int(W), C.c_int(ch), _p(out))
+    return out
+
+
+def normalize_lut(smin, smax, use_fma=True):
+    lut = np.empty(256, np.uint8)
+    lib().orc_normalize_lut(C.c_int(smin), C.c_int(smax), C.c_int(int(use_fma)), _p(lut))
+    return lut
+
+
+def normalize(img, use_fma=True, return_minmax=False):
+    img = _u8(img); out = np.empty_like(img); mn = C.c_int(); mx = C.c_int()
+    lib().orc_normalize(_p(img), C.c_long(img.size), C.c_int(int(use_fma)), _p(out), C.byref(mn), C.byref(mx))
+    return (out, mn.value, mx.value) if return_minmax else out
+
+
+def gray(bgr):
+    H, W, _ = bgr.shape
+    assert bgr.dtype == np.uint8 and bgr.strides[2] == 1 and bgr.strides[1] == 3
+    out = np.empty((H, W), np.uint8)
+    lib().orc_gray(_p(bgr), C.c_int(H), C.c_int(W), C.c_long(bgr.strides[0]), _p(out))
+    return out
+
+
+def gaussian(g, k=5):
+    assert g.dtype == np.uint8 and g.ndim == 2 and g.strides[1] == 1
+    H, W = g.shape; out = np.empty((H, W), np.uint8)
+    if lib().orc_gaussian(_p(g), C.c_int(H), C.c_int(W), C.c_long(g.strides[0]), C.c_int(k), _p(out)):
+        raise ValueError("bad gaussian k=%r" % (k,))
+    return out
+
+
+def hist256(img):
+    img = _u8(img); h = np.empty(256, np.int32)
+    lib().orc_hist256(_p(img), C.c_long(img.size), _p(h))
+    return h
+
+
+def otsu_from_hist(h, n):
+    h = np.ascontiguousarray(h, np.int32)
+    return lib().orc_otsu_from_hist(_p(h), C.c_long(int(n)))
+
+
+def threshold(img, T):
+    img = _u8(img); out = np.empty_like(img)
+    lib().orc_threshold(_p(img), C.c_long(img.size), C.c_int(int(T)), _p(out))
+    return out
+
+
+def prepare_analysis(bgr, return_all=False):
+    bgr = _u8(bgr); H, W, _ = bgr.shape
+    g = np.empty((H, W), np.uint8); bl = np.empty((H, W), np.uint8); b = np.empty((H, W), np.uint8)
+    T = lib().orc_prepare_analysis(_p(bgr), C.c_int(H), C.c_int(W), _p(g), _p(bl), _p(b))
+    return (g, b, T, bl) if return_all else (g, b)
+
+
+def process_pipeline(bgr, use_fma=True):
+    bgr = _u8(bgr); H, W, _ = bgr.shape; out = np.empty_like(bgr)
+    lib().orc_process_pipeline(_p(bgr), C.c_int(H), C.c_int(W), C.c_int(int(use_fma)), _p(out))
+    return out
+
+
+# --- warp -----------------------------------------------------------------------
+def get_perspective(src_pts, dst_pts):
+    s = np.ascontiguousarray(np.asarray(src_pts, np.float32).reshape(4, 2))
+    d = np.ascontiguousarray(np.asarray(dst_pts, np.float32).reshape(4, 2))
+    M = np.empty(9, np.float64)
+    if lib().orc_get_perspective(_p(s), _p(d), _p(M)):
+        raise ValueError("degenerate quadrilateral")
+    return M.reshape(3, 3)
+
+
+def invert3(M):
+    M = np.ascontiguousarray(M, np.float64); out = np.empty(9, np.float64)
+    if lib().orc_invert3(_p(M), _p(out)):
+        raise ValueError("singular matrix")
+    return out.reshape(3, 3)
+
+
+def warp(bgr, M, size):
+    """cv2.warpPerspective(bgr, M, (size_w, size_h)) with INTER_LINEAR / BORDER_CONSTANT 0."""
+    bgr = _u8(bgr); H, W, _ = bgr.shape
+    sw, sh = (size, size) if np.isscalar(size) else size
+    Mi = np.ascontiguousarray(invert3(M))
+    out = np.empty((sh, sw, 3), np.uint8)
+    lib().orc_warp(_p(bgr), C.c_int(H), C.c_int(W), _p(Mi), C.c_int(sh), C.c_int(sw), _p(out))
+    return out
+
+
+def warp_image(bgr, points, display_size=(1280, 720), margin=100):
+    """board_detection.warp_image (board_detection.py:61-71)."""
+    S = min(display_size) - margin
+    M = get_perspective(points, [[0, 0], [S, 0], [0, S], [S, S]])
+    return warp(bgr, M, S), M, S
+
+
+# --- per-square --------------------------------------------------------------------
+class PdStats(C.Structure):
+    _fields_ = [("n", C.c_int64), ("sum", C.c_int64), ("sumsq", C.c_int64), ("sad", C.c_int64),
+                ("center_sum", C.c_int64), ("center_cnt", C.c_int64),
+                ("border_sum", C.c_int64), ("border_cnt", C.c_int64),
+                ("ring_sum", C.c_int64 * 4), ("ring_cnt", C.c_int64 * 4)]
+
+
+def square_preprocess(sq, k=5):
+    assert sq.dtype == np.uint8
+    h, w = sq.shape[:2]
+    ch = 1 if sq.ndim == 2 else 3
+    assert sq.strides[-1] == 1 and (ch == 1 or sq.strides[1] == 3)
+    out = np.empty((h, w), np.uint8)
+    if lib().orc_square_preprocess(_p(sq), C.c_int(h), C.c_int(w), C.c_int(ch), C.c_long(sq.strides[0]),
+                                   C.c_int(k), _p(out)):
+        raise ValueError("bad gaussian k")
+    return out
+
+
+def square_masks(h, w):
+    m = np.empty((h, w), np.uint8)
+    lib().orc_square_masks(C.c_int(h), C.c_int(w), _p(m))
+    return m
+
+
+def pd_square_stats(g, ref=None):
+    g = _u8(g); h, w = g.shape
+    st = PdStats()
+    r = _u8(ref) if ref is not None else None
+    lib().orc_pd_square_stats(_p(g), _p(r) if r is not None else None, C.c_int(h), C.c_int(w), C.byref(st))
+    return {"n": st.n, "sum": st.sum, "sumsq": st.sumsq, "sad": st.sad,
+            "center_sum": st.center_sum, "center_cnt": st.center_cnt,
+            "border_sum": st.border_sum, "border_cnt": st.border_cnt,
+            "ring_sum": list(st.ring_sum), "ring_cnt": list(st.ring_cnt)}
+
+
+def cd_calibrate(g, initial_variance=100.0):
+    g = _u8(g); m = np.empty(g.shape, np.float32); v = np.empty(g.shape, np.float32)
+    lib().orc_cd_calibrate(_p(g), C.c_long(g.size), C.c_float(initial_variance), _p(m), _p(v))
+    return m, v
+
+
+def cd_update(g, mean, var, alpha=0.1):
+    """In-place EMA update; alpha as the reference computes it: f32(alpha), f32(1 - alpha)."""
+    g = _u8(g)
+    assert mean.dtype == np.float32 and var.dtype == np.float32 and mean.flags.c_contiguous and var.flags.c_contiguous
+    lib().orc_cd_update(_p(g), C.c_long(g.size), C.c_float(np.float32(alpha)), C.c_float(np.float32(1 - alpha)),
+                        _p(mean), _p(var))
+
+
+def cd_detect(g, mean, var, z_threshold=2.5):
+    g = _u8(g); mean = np.ascontiguousarray(mean, np.float32); var = np.ascontiguousarray(var, np.float32)
+    cnt = C.c_int64(); zmax = C.c_float()
+    lib().orc_cd_detect(_p(g), C.c_long(g.size), _p(mean), _p(var), C.c_float(np.float32(z_threshold)),
+                        C.byref(cnt), C.byref(zmax))
+    return cnt.value, zmax.value

@@ -1,0 +1,183 @@
+"""GPU parity: warp_image, 64-square split and the per-square PieceDetector /
+ChangeDetector statistics through the C ABI vs the CPU oracle (all bit-exact:
+integer sums, IEEE f32 sqrt/div/mul/add without contraction)."""
+import numpy as np
+import pytest
+
+from chessboard_vision_b200 import synth
+from chessboard_vision_b200.engine import (grid_rects, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT,
+                                           SQ_CD_UPDATE)
+from chessboard_vision_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_perspective_matrix_matches_oracle(engine, oracle):
+    rng = np.random.default_rng(1)
+    for i in range(200):
+        pts = np.float32([[0, 0], [1920, 0], [0, 1080], [1920, 1080]]) + rng.uniform(-300, 300, (4, 2)).astype(np.float32)
+        dst = np.float32([[0, 0], [620, 0], [0, 620], [620, 620]])
+        assert np.array_equal(engine.get_perspective_transform(pts, dst), oracle.get_perspective(pts, dst))
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (1080, 1920), (2160, 3840)])
+def test_warp_calibration_corners(engine, oracle, shape):
+    H, W = shape
+    img = synth.noise_frame(H, W, 0)
+    pts = synth.calib_points(H, W)
+    M = engine.get_perspective_transform(pts, [[0, 0], [620, 0], [0, 620], [620, 620]])
+    assert np.array_equal(engine.warp(img, M, 620), oracle.warp(img, M, 620))
+
+
+def test_warp_out_of_frame_and_batch(engine, oracle):
+    img = synth.frame_batch(2, 240, 320, "noise", 3)
+    pts = np.float32([[-50, -30], [300, 10], [20, 260], [350, 250]])
+    M = oracle.get_perspective(pts, [[0, 0], [100, 0], [0, 100], [100, 100]])
+    got = engine.warp(img, M, 100)
+    for i in range(2):
+        assert np.array_equal(got[i], oracle.warp(img[i], M, 100))
+    # one matrix per frame, rectangular output
+    M2 = np.stack([M, oracle.get_perspective(pts + 7, [[0, 0], [100, 0], [0, 100], [100, 100]])])
+    got = engine.warp(img, M2, (90, 70))
+    for i in range(2):
+        assert np.array_equal(got[i], oracle.warp(img[i], M2[i], (90, 70)))
+
+
+def _oracle_square_stats(oracle, board, rects, ref_plane=None, k=5):
+    out = []
+    for (x, y, w, h) in rects:
+        sq = board[y:y + h, x:x + w]
+        g = oracle.square_preprocess(sq, k)
+        ref = None if ref_plane is None else np.ascontiguousarray(ref_plane[y:y + h, x:x + w])
+        out.append((g, oracle.pd_square_stats(g, ref)))
+    return out
+
+
+def _check_pd(st, o, has_ref):
+    assert st["n"] == o["n"] and st["sum"] == o["sum"] and st["sumsq"] == o["sumsq"]
+    assert st["center_sum"] == o["center_sum"] and st["center_cnt"] == o["center_cnt"]
+    assert st["border_sum"] == o["border_sum"] and st["border_cnt"] == o["border_cnt"]
+    assert list(st["ring_sum"]) == o["ring_sum"] and list(st["ring_cnt"]) == o["ring_cnt"]
+    assert st["has_ref"] == int(has_ref)
+    if has_ref:
+        assert st["sad"] == o["sad"]
+
+
+@pytest.mark.parametrize("grid", ["linear", "smart"])
+def test_pd_stats_and_reference(engine, oracle, grid):
+    board = synth.board_frame(620, 620, 2)
+    board2 = synth.board_frame(620, 620, 3)
+    if grid == "linear":
+        rects, keys = grid_rects(620)
+    else:
+        rects, keys = grid_rects(620, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    assert len(rects) == 64 and keys[0] == (0, 7) and keys[-1] == (7, 0)
+    st = engine.new_state(1, 620, 620)
+    p = engine.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF)
+    s1 = engine.squares(board, rects, p, st)[0]
+    o1 = _oracle_square_stats(oracle, board, rects)
+    for i in range(64):
+        _check_pd(s1[i], o1[i][1], False)
+    # reference plane now holds the preprocessed squares
+    ref_plane = st.get(0, _lib.PLANE_PD_REF)
+    for i, (x, y, w, h) in enumerate(rects):
+        assert np.array_equal(ref_plane[y:y + h, x:x + w], o1[i][0])
+    # second frame: SAD against the stored reference, no update
+    p2 = engine.square_params(ops=SQ_PD_STATS)
+    s2 = engine.squares(board2, rects, p2, st)[0]
+    o2 = _oracle_square_stats(oracle, board2, rects, ref_plane)
+    for i in range(64):
+        _check_pd(s2[i], o2[i][1], True)
+    # selective reference update
+    sel = np.zeros(64, np.uint8); sel[[3, 17]] = 1
+    engine.squares(board2, rects, engine.square_params(ops=SQ_PD_SET_REF), st, select=sel, want_stats=False)
+    ref2 = st.get(0, _lib.PLANE_PD_REF)
+    for i, (x, y, w, h) in enumerate(rects):
+        want = o2[i][0] if sel[i] else o1[i][0]
+        assert np.array_equal(ref2[y:y + h, x:x + w], want)
+    st.free()
+
+
+@pytest.mark.parametrize("cd_blur", [5, 13, 1])
+def test_cd_calibrate_detect_update(engine, oracle, cd_blur):
+    rects, _ = grid_rects(620, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    b0 = synth.board_frame(620, 620, 4)
+    b1 = b0.copy()
+    b1[100:300, 150:420] = 255          # a "hand"
+    b1[400:440, 10:60] //= 2
+    st = engine.new_state(2, 620, 620)   # use slot 1 to exercise stream0
+    pc = engine.square_params(ops=SQ_CD_CALIBRATE, cd_blur=cd_blur, initial_variance=100)
+    engine.squares(b0, rects, pc, st, stream0=1, want_stats=False)
+    mean = st.get(1, _lib.PLANE_CD_MEAN); var = st.get(1, _lib.PLANE_CD_VAR)
+    om, ov, og1 = {}, {}, {}
+    for i, (x, y, w, h) in enumerate(rects):
+        g0 = oracle.square_preprocess(b0[y:y + h, x:x + w], cd_blur)
+        m, v = oracle.cd_calibrate(g0, 100.0)
+        assert np.array_equal(mean[y:y + h, x:x + w], m) and np.array_equal(var[y:y + h, x:x + w], v)
+        om[i], ov[i] = m, v
+        og1[i] = oracle.square_preprocess(b1[y:y + h, x:x + w], cd_blur)
+    # detect + update in one call
+    pd = engine.square_params(ops=SQ_CD_DETECT | SQ_CD_UPDATE, cd_blur=cd_blur, z_threshold=2.5, alpha=0.1)
+    s = engine.squares(b1, rects, pd, st, stream0=1)[0]
+    mean = st.get(1, _lib.PLANE_CD_MEAN); var = st.get(1, _lib.PLANE_CD_VAR)
+    for i, (x, y, w, h) in enumerate(rects):
+        cnt, zmax = oracle.cd_detect(og1[i], om[i], ov[i], 2.5)
+        assert s[i]["cd_valid"] == 1
+        assert s[i]["cd_changed"] == cnt
+        assert s[i]["cd_zmax"] == np.float32(zmax)
+        oracle.cd_update(og1[i], om[i], ov[i], 0.1)
+        assert np.array_equal(mean[y:y + h, x:x + w], om[i]) and np.array_equal(var[y:y + h, x:x + w], ov[i])
+    # slot 0 never calibrated: CD not valid there
+    s0 = engine.squares(b1, rects, engine.square_params(ops=SQ_CD_DETECT, cd_blur=cd_blur), st, stream0=0)[0]
+    assert not s0["cd_valid"].any()
+    st.free()
+
+
+def test_cd_focus_squares_and_gray_atlas(engine, oracle):
+    """test_change_detector_regression.py:31-54 in kernel form: 64 gray 50x50 squares, one goes 0 -> 255."""
+    rects = [(c * 50, r * 50, 50, 50) for r in range(8) for c in range(8)]
+    atlas0 = np.zeros((400, 400), np.uint8)
+    atlas1 = atlas0.copy(); atlas1[3 * 50:4 * 50, 3 * 50:4 * 50] = 255
+    st = engine.new_state(1, 400, 400)
+    engine.squares(atlas0, rects, engine.square_params(ops=SQ_CD_CALIBRATE), st, want_stats=False)
+    s = engine.squares(atlas1, rects, engine.square_params(ops=SQ_CD_DETECT), st)[0]
+    idx = 3 * 8 + 3
+    pct = s["cd_changed"] / s["n"] * 100
+    assert pct[idx] > 75 and (np.delete(pct, idx) == 0).all()
+    # focus: only selected squares are evaluated
+    sel = np.zeros(64, np.uint8); sel[5] = 1
+    s = engine.squares(atlas1, rects, engine.square_params(ops=SQ_CD_DETECT), st, select=sel)[0]
+    assert s["cd_valid"][5] == 1 and s["cd_valid"].sum() == 1
+    st.free()
+
+
+def test_squares_errors(engine):
+    board = np.zeros((100, 100, 3), np.uint8)
+    with pytest.raises(ValueError):
+        engine.squares(board, [(90, 90, 20, 20)], engine.square_params())
+    with pytest.raises(Exception):
+        engine.squares(board, [(0, 0, 20, 20)], engine.square_params(ops=SQ_CD_DETECT))   # needs state
+
+
+def test_full_pipeline_matches_composition(engine, oracle):
+    """cvb_pipeline (host buffers) == oracle composition enhance -> warp -> squares, on 2 small frames."""
+    H, W = 270, 480
+    frames = synth.frame_batch(2, H, W, "board", 20)
+    pts = synth.calib_points(H, W)
+    S = 160
+    M = oracle.get_perspective(pts, [[0, 0], [S, 0], [0, S], [S, S]])
+    rects, _ = grid_rects(S)
+    st = engine.new_state(2, S, S)
+    pp = engine.pipeline_params(squares=engine.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE | SQ_CD_DETECT),
+                                board_size=S)
+    T, stats = engine.pipeline(frames, M, rects, pp, st)
+    for i in range(2):
+        enh = oracle.process_pipeline(frames[i], True)
+        _, _, rT, _ = oracle.prepare_analysis(enh, True)
+        assert T[i] == rT
+        board = oracle.warp(enh, M, S)
+        o = _oracle_square_stats(oracle, board, rects)
+        for j in range(64):
+            _check_pd(stats[i, j], o[j][1], False)
+            assert stats[i, j]["cd_valid"] == 1 and stats[i, j]["cd_changed"] == 0
+    st.free()
