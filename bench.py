@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the ChessVision hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (OpenCV)
+
+A "step" is one pass of the full path (enhance chain + Otsu analysis + warp +
+64 squares + PieceDetector statistics + ChangeDetector detect/update) over one
+batch of synthetic 1080p BGR frames (BASELINE.json configs[3]: 256 frames per
+GPU; weak scaling: every rank owns its own 256 frames and its own per-stream
+state, no data-path collective).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "1080p frames/sec/GPU full enhance+grid+change pipeline; HBM GB/s vs roofline"
+H, W, S = 1080, 1920, 620
+UNIQUE = 16        # distinct synthetic frames, tiled to the batch (content does not change the work)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference leg (oracle/ is only touched here: cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    kind, seeds = args
+    from chessboard_vision_b200 import synth
+    pts = synth.calib_points(H, W)
+    n = 0
+    if kind == "cv2":
+        import cv2
+        from oracle import ref_cv2
+        cv2.setNumThreads(1)
+        cd = {}
+        for s in seeds:
+            ref_cv2.full_frame(_FRAMES[s % len(_FRAMES)], pts, cd_state=cd, pd_ref=None)
+            n += 1
+    else:
+        import oracle as O
+        M = O.get_perspective(pts, [[0, 0], [S, 0], [0, S], [S, S]])
+        for s in seeds:
+            f = _FRAMES[s % len(_FRAMES)]
+            enh = O.process_pipeline(f, True)
+            O.prepare_analysis(enh)
+            board = O.warp(enh, M, S)
+            for r in range(8):
+                for c in range(8):
+                    g = O.square_preprocess(board[r * 77:(r + 1) * 77, c * 77:(c + 1) * 77], 5)
+                    O.pd_square_stats(g)
+                    m, v = O.cd_calibrate(g)
+                    O.cd_detect(g, m, v)
+                    O.cd_update(g, m, v)
+            n += 1
+    return n
+
+
+_FRAMES = None
+
+
+def cpu_reference(frames, n_frames, pool, kind):
+    """Frames/s of the reference CPU path over `n_frames` frames using every host core
+    (one process per core, one OpenCV thread each: BASELINE.md section 3c)."""
+    workers = pool._processes
+    chunks = [list(range(i, n_frames, workers)) for i in range(workers)]
+    chunks = [(kind, c) for c in chunks if c]
+    t0 = time.perf_counter()
+    done = sum(pool.map(_cpu_worker, chunks))
+    dt = time.perf_counter() - t0
+    return done / dt, dt
+
+
+def make_pool(frames):
+    """Fork-based pool created BEFORE any CUDA context exists in this process."""
+    import multiprocessing as mp
+    global _FRAMES
+    _FRAMES = frames
+    try:
+        import cv2  # noqa: F401
+        kind = "cv2"
+    except Exception:
+        kind = "port"
+        import oracle as O
+        O.lib()
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("fork").Pool(cores)
+    pool.map(_cpu_worker, [(kind, [0])] * cores)     # warm every worker (imports, tables)
+    return pool, kind, cores
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            # under load = the upper half of the samples (the sampler also sees the idle edges)
+            hi = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=float(np.median(hi)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--kind", default="board", choices=["board", "noise"])
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0: 4 per host core)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from chessboard_vision_b200 import synth
+
+    config = {"workload": "BASELINE.json configs[3]: batch of %d synthetic 1080p BGR frames per GPU, full pipeline "
+                          "(LAB+CLAHE+bilateral d=9+sharpen+normalize, gray+blur+Otsu mask, warp to 620x620, 64 squares, "
+                          "piece_detector statistics + change_detector detect/update)" % args.frames,
+              "frames_per_gpu": args.frames, "height": H, "width": W, "frame_kind": args.kind,
+              "unique_frames": UNIQUE, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+              "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU vs 126 MB)" % (args.frames * H * W * 3 / 1e6)}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        frames = synth.frame_batch(UNIQUE, H, W, args.kind, 0)
+        pool, kind, cores = make_pool(frames)
+        per_step = args.cpu_frames or 2 * cores
+        for _ in range(args.warmup):
+            cpu_reference(frames, per_step, pool, kind)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_reference(frames, per_step, pool, kind)
+        dt = time.perf_counter() - t0
+        pool.close()
+        fps = per_step * args.steps / dt
+        sample = "%d frames per step (of the %d-frame batch), %d processes x 1 OpenCV thread" % (per_step, args.frames, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (f32 bilateral / CLAHE blend, f64 Otsu and warp coordinates)", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores,
+                             "kind": "port", "sample": sample,
+                             "what": ("oracle/ref_cv2.py: the reference's own cv2/numpy call sequence on OpenCV %s" %
+                                      __import__("cv2").__version__) if kind == "cv2" else
+                                     "oracle/cvb_oracle.c scalar C restatement (cv2 not importable)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ this repo's arm
+    frames_u = synth.frame_batch(UNIQUE, H, W, args.kind, 0)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        pool, kind, cores = make_pool(frames_u)          # fork before CUDA
+        n_cpu = args.cpu_frames or 4 * cores
+        fps_cpu, dt_cpu = cpu_reference(frames_u, n_cpu, pool, kind)
+        pool.close()
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d of the %d frames of one step, %.1f s wall, %d processes x 1 OpenCV thread" %
+                         (n_cpu, args.frames, dt_cpu, cores),
+               "what": "oracle/ref_cv2.py (reference call sequence on cv2/numpy)" if kind == "cv2"
+                       else "oracle/cvb_oracle.c scalar C restatement"}
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from chessboard_vision_b200.engine import (Engine, grid_rects, STATS_DTYPE, SQ_PD_STATS, SQ_PD_SET_REF,
+                                               SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
+    eng = Engine(local_rank)
+    n = args.frames
+    rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    M = eng.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
+    state = eng.new_state(n, S, S)
+
+    # host batch in pinned memory (e2e source) and a resident device copy (kernel-only source)
+    host = eng.pinned((n, H, W, 3))
+    for i in range(n):
+        host[i] = frames_u[(i + rank) % UNIQUE]
+    d_in = eng.empty((n, H, W, 3))
+    eng.lib.cvb_memcpy_h2d(eng.h, d_in.ptr, host.ctypes.data, host.nbytes)
+    d_stats = eng.empty((n, len(rects)), STATS_DTYPE)
+    d_otsu = eng.empty((n,), np.int32)
+    eng.synchronize()
+
+    sq_cal = eng.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE)
+    sq_run = eng.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE)
+    pp_cal = eng.pipeline_params(squares=sq_cal, board_size=S)
+    pp = eng.pipeline_params(squares=sq_run, board_size=S)
+    # calibration frame: references + background model for every stream slot (untimed)
+    eng.pipeline_dev(d_in, M, rects, pp_cal, state, stats=d_stats, otsu_t=d_otsu)
+    eng.synchronize()
+
+    def barrier():
+        eng.synchronize()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run_dev(k):
+        for _ in range(k):
+            eng.pipeline_dev(d_in, M, rects, pp, state, stats=d_stats, otsu_t=d_otsu)
+
+    def run_e2e(k):
+        for _ in range(k):
+            eng.lib  # the public host-buffer call: H2D + kernels + D2H of per-square results
+            eng.pipeline(host, M, rects, pp, state)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = eng.event(), eng.event()
+        l0 = eng.launch_count()
+        eng.record(e0)
+        fn(k)
+        eng.record(e1)
+        ms = eng.elapsed_ms(e0, e1)
+        barrier()
+        launches = eng.launch_count() - l0
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    run_dev(args.warmup)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, launches = timed(run_dev, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel device time (CUDA events around every launch, same K steps) -> roofline of the dominant kernel
+    eng.profile(True)
+    run_dev(args.steps)
+    prof = eng.profile_read()
+    eng.profile(False)
+
+    run_e2e(args.warmup)
+    ms_e2e, _ = timed(run_e2e, args.steps)
+
+    total_frames = n * args.steps * world
+    value = total_frames / (ms_dev / 1e3)
+    e2e = total_frames / (ms_e2e / 1e3)
+    if rank == 0:
+        npx = H * W
+        peak, peak_src = peaks()
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        # algorithmic bytes per frame per kernel
+        alg = {"k_tile_hist": 3 * npx, "k_fused": 6 * npx, "k_finish": 8 * npx, "k_threshold": 2 * npx,
+               "k_warp": 1012 * 916 * 3 + S * S * 3, "k_squares": S * S * 3 + 64 * 77 * 77 * (1 + 4 + 4 + 4 + 4 + 1),
+               "k_clahe_lut": 64 * 256 * 5, "k_otsu": 1024}
+        stages = {}
+        for name, (ms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            per_launch_ms = ms / cnt
+            b = alg.get(name, 0) * n
+            stages[name] = {"ms_per_launch": per_launch_ms, "share": ms / tot_ms, "launches": cnt,
+                            "alg_bytes_per_launch": b, "achieved_gbs": b / per_launch_ms / 1e6,
+                            "frac_of_hbm_peak": b / per_launch_ms / 1e6 / peak}
+        dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+        d = stages[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "note": "k_fused is bound by the FP32/LSU pipes (49-tap bilateral, ~700 ops per pixel), not by HBM; "
+                            "its HBM fraction is reported as the contract asks, the per-stage table gives the streaming "
+                            "kernels' fractions", "stages": stages}
+        fp32_ops = 49 * 8 * npx * n       # 49 taps x (vabsdiff, LUT load, mul, add, 3 fma, convert) per pixel, lower bound
+        roofline["fp32_pipe"] = {"ops_per_launch_lower_bound": fp32_ops,
+                                 "achieved_tops": fp32_ops / (stages["k_fused"]["ms_per_launch"] / 1e3) / 1e12
+                                 if "k_fused" in stages else None,
+                                 "peak_tflops_fp32": 148 * 128 * 2 * 1.965e9 / 1e12}
+        out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8 (f32 bilateral / CLAHE blend, f64 Otsu and warp coordinates)",
+               "data": "synthetic", "config": config, "per_gpu": value / world,
+               "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.nbytes),
+                       "d2h_bytes_per_step": int(n * len(rects) * STATS_DTYPE.itemsize + n * 4),
+                       "ms_per_step": ms_e2e / args.steps,
+                       "api": "Engine.pipeline -> cvb_pipeline (pinned host frames in, per-square statistics + Otsu "
+                              "thresholds out)"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,8 @@ SYMBOLS = [
     ("cvb_set_stream", _I, [_P, _P]),
     ("cvb_synchronize", _I, [_P]),
     ("cvb_launch_count", C.c_int64, [_P]),
+    ("cvb_profile_enable", _I, [_P, _I]),
+    ("cvb_profile_read", _I, [_P, _P, _P, _P, _I, C.POINTER(_I)]),
     ("cvb_malloc", _I, [_P, _SZ, C.POINTER(_P)]),
     ("cvb_free", _I, [_P, _P]),
     ("cvb_host_alloc", _I, [_SZ, C.POINTER(_P)]),

@@ -33,6 +33,24 @@ int cvb_ws(cvb_handle *h, DevBuf &b, size_t bytes, void **out)
     return CVB_OK;
 }
 
+void cvb_prof_begin(cvb_handle *h, const char *name)
+{
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, h->stream);
+    h->prof.push_back(r);
+}
+void cvb_prof_end(cvb_handle *h)
+{
+    if (!h->prof.empty()) cudaEventRecord(h->prof.back().e1, h->stream);
+}
+static void prof_clear(cvb_handle *h)
+{
+    for (ProfRec &r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    h->prof.clear();
+}
+
 #define WS(buf, type, count, var) \
     type *var = nullptr;          \
     CVB_TRY(cvb_ws(h, h->buf, sizeof(type) * (size_t)(count), (void **)&var))
@@ -101,6 +119,7 @@ void cvb_destroy(cvb_handle *h)
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    prof_clear(h);
     drop_rect_cache(h);
     delete h;
 }
@@ -119,6 +138,39 @@ int cvb_synchronize(cvb_handle *h)
     return CVB_OK;
 }
 int64_t cvb_launch_count(cvb_handle *h) { return h ? h->launches : -1; }
+
+int cvb_profile_enable(cvb_handle *h, int on)
+{
+    REQ_H(h);
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    prof_clear(h);
+    h->profiling = on != 0;
+    return CVB_OK;
+}
+int cvb_profile_read(cvb_handle *h, char *names32, float *total_ms, int *counts, int max_entries, int *n_out)
+{
+    REQ_H(h);
+    CVB_REQUIRE(names32 && total_ms && counts && n_out && max_entries > 0, "null pointer");
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    int n = 0;
+    for (const ProfRec &r : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        int k = 0;
+        for (; k < n; ++k)
+            if (strncmp(names32 + 32 * k, r.name, 31) == 0) break;
+        if (k == n) {
+            if (n == max_entries) continue;
+            memset(names32 + 32 * k, 0, 32);
+            strncpy(names32 + 32 * k, r.name, 31);
+            total_ms[k] = 0.f; counts[k] = 0;
+            ++n;
+        }
+        total_ms[k] += ms; counts[k] += 1;
+    }
+    *n_out = n;
+    return CVB_OK;
+}
 
 int cvb_malloc(cvb_handle *h, size_t bytes, void **dptr)
 {
@@ -409,8 +461,14 @@ int cvb_enhance(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cv
 }
 
 // ---- warp ------------------------------------------------------------------------------------
+static std::map<cvb_handle *, std::vector<double>> g_mat_cache;
 static int upload_inverse_mats(cvb_handle *h, const double *M9, int n_mats, double **d_out)
 {
+    std::vector<double> &last = g_mat_cache[h];
+    if (h->ws_mats.p && last.size() == (size_t)n_mats * 9 && memcmp(last.data(), M9, sizeof(double) * 9 * n_mats) == 0) {
+        *d_out = (double *)h->ws_mats.p;      // same matrices as the previous call: already resident
+        return CVB_OK;
+    }
     std::vector<double> inv((size_t)n_mats * 9);
     for (int i = 0; i < n_mats; ++i)
         if (cvb_host_invert3(M9 + 9 * i, inv.data() + 9 * i) != CVB_OK) {
@@ -420,6 +478,7 @@ static int upload_inverse_mats(cvb_handle *h, const double *M9, int n_mats, doub
     WS(ws_mats, double, (size_t)n_mats * 9, d_m);
     CVB_CHECK_CUDA(cudaMemcpyAsync(d_m, inv.data(), sizeof(double) * 9 * n_mats, cudaMemcpyHostToDevice, h->stream));
     CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // `inv` dies at return
+    last.assign(M9, M9 + (size_t)n_mats * 9);
     *d_out = d_m;
     return CVB_OK;
 }
@@ -522,7 +581,7 @@ struct RectCache {
 };
 static std::map<cvb_handle *, RectCache> g_rect_cache;
 } // extern "C" (paused: C++ linkage for the helper below)
-static void drop_rect_cache(cvb_handle *h) { g_rect_cache.erase(h); }
+static void drop_rect_cache(cvb_handle *h) { g_rect_cache.erase(h); g_mat_cache.erase(h); }
 extern "C" {
 
 static int stage_rects(cvb_handle *h, const cvb_rect *rects, int n_sq, const uint8_t *select, int BH, int BW,
@@ -643,9 +702,14 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, con
     if (!binary) CVB_TRY(cvb_ws(h, h->ws_bin, npx * n, (void **)&binary));
     if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
     if (!warped) CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * n, (void **)&warped));
-    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
+    // small host->device staging first (it synchronises), then only kernel launches
     double *d_m = nullptr;
     CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
+    {
+        cvb_rect *d_rects; int32_t *d_ofs; uint8_t *d_masks, *d_select; int max_px;
+        CVB_TRY(stage_rects(h, rects, n_sq, select, S, S, &d_rects, &d_ofs, &d_masks, &d_select, &max_px));
+    }
+    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
     CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_m, n_mats, S, S, warped));
     return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
 }

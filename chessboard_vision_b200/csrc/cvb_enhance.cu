@@ -16,11 +16,6 @@
 #include "cvb_device.cuh"
 #include <cfloat>
 
-#define LAUNCH_CHECK(h)                                  \
-    do {                                                 \
-        (h)->launches++;                                 \
-        CVB_CHECK_CUDA(cudaGetLastError());              \
-    } while (0)
 
 int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g)
 {
@@ -85,12 +80,14 @@ static int grid_for(cvb_handle *h, long items, int per_block)
 }
 int launch_bgr2lab(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *lab)
 {
+    PROF(h, "k_lab_pointwise");
     k_lab_pointwise<true><<<grid_for(h, npx, 256), 256, 0, h->stream>>>(bgr, npx, h->d_tables, lab);
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
 int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr)
 {
+    PROF(h, "k_lab_pointwise");
     k_lab_pointwise<false><<<grid_for(h, npx, 256), 256, 0, h->stream>>>(lab, npx, h->d_tables, bgr);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -155,6 +152,7 @@ int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int
     int splits = (4 * h->sm_count + tiles * n - 1) / (tiles * n);
     splits = max(1, min(splits, (g.tile_h + 7) / 8));
     dim3 grid(tiles, splits, n);
+    PROF(h, "k_tile_hist");
     if (from_bgr) k_tile_hist<true><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
     else k_tile_hist<false><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
     LAUNCH_CHECK(h);
@@ -203,6 +201,7 @@ __global__ void __launch_bounds__(256) k_clahe_lut(const int32_t *__restrict__ h
 }
 int launch_clahe_lut(cvb_handle *h, const int32_t *hist, int n, const ClaheGeom &g, uint8_t *lut)
 {
+    PROF(h, "k_clahe_lut");
     k_clahe_lut<<<g.tiles_x * g.tiles_y * n, 256, 0, h->stream>>>(hist, g, lut);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -223,6 +222,7 @@ int launch_clahe_apply_plane(cvb_handle *h, const uint8_t *src, int n, int H, in
                              const uint8_t *lut, uint8_t *dst)
 {
     dim3 grid((W + 63) / 64, (H + 3) / 4, n);
+    PROF(h, "k_clahe_apply_plane");
     k_clahe_apply_plane<<<grid, 256, 0, h->stream>>>(src, H, W, g, lut, dst);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -450,6 +450,7 @@ static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
         attr_done = true;
     }
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, n);
+    PROF(h, "k_fused");
     kern<<<grid, 256, Cfg::smem_bytes, h->stream>>>(a);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -530,10 +531,12 @@ __global__ void __launch_bounds__(256) k_minmax(const uint8_t *__restrict__ src,
 }
 int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, int32_t *minmax)
 {
+    PROF(h, "k_minmax_init");
     k_minmax_init<<<(n + 255) / 256, 256, 0, h->stream>>>(minmax, n);
     LAUNCH_CHECK(h);
     int bx = stream_blocks(bytes_per_frame / 16, 8 * h->sm_count / (n > 0 ? n : 1));
     dim3 grid(bx, n);
+    PROF(h, "k_minmax");
     k_minmax<<<grid, 256, 0, h->stream>>>(src, bytes_per_frame, minmax);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -565,6 +568,7 @@ int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_fr
 {
     int bx = stream_blocks(bytes_per_frame / 16, 16 * h->sm_count / (n > 0 ? n : 1));
     dim3 grid(bx, n);
+    PROF(h, "k_normalize");
     k_normalize<<<grid, 256, 0, h->stream>>>(src, bytes_per_frame, minmax, out);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -578,6 +582,7 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t *__restrict__ bgr, l
 }
 int launch_gray(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *gray)
 {
+    PROF(h, "k_gray");
     k_gray<<<grid_for(h, npx, 256), 256, 0, h->stream>>>(bgr, npx, gray);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -626,6 +631,7 @@ int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int 
     }
     gk.k = ksize;
     dim3 grid((W + 63) / 64, (H + 15) / 16, n);
+    PROF(h, "k_gaussian");
     k_gaussian<<<grid, 256, 0, h->stream>>>(src, H, W, gk, dst);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -761,6 +767,7 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
 {
     if (hist) CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * (size_t)n, h->stream));
     dim3 grid((W + 127) / 128, (H + 15) / 16, n);
+    PROF(h, "k_finish");
     if (minmax) k_finish<true><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
     else k_finish<false><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);
     LAUNCH_CHECK(h);
@@ -803,6 +810,7 @@ __global__ void __launch_bounds__(32) k_otsu(const int32_t *__restrict__ hist, l
 }
 int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t)
 {
+    PROF(h, "k_otsu");
     k_otsu<<<n, 32, 0, h->stream>>>(hist, npx, otsu_t);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -836,6 +844,7 @@ int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const i
 {
     int bx = stream_blocks(npx / 16, 16 * h->sm_count / (n > 0 ? n : 1));
     dim3 grid(bx, n);
+    PROF(h, "k_threshold");
     k_threshold<<<grid, 256, 0, h->stream>>>(src, npx, otsu_t, dst);
     LAUNCH_CHECK(h);
     return CVB_OK;

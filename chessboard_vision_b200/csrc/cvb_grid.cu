@@ -9,11 +9,6 @@
 
 static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the ABI");
 
-#define LAUNCH_CHECK(h)                                  \
-    do {                                                 \
-        (h)->launches++;                                 \
-        CVB_CHECK_CUDA(cudaGetLastError());              \
-    } while (0)
 
 // ---------------------------------------------------------------------------------------
 // cv2.warpPerspective, INTER_LINEAR, BORDER_CONSTANT(0)  (imgwarp.cpp
@@ -67,6 +62,7 @@ int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const do
                 int out_w, uint8_t *warped)
 {
     dim3 grid((out_w + 63) / 64, (out_h + 3) / 4, n);
+    PROF(h, "k_warp");
     k_warp<<<grid, 256, 0, h->stream>>>(bgr, H, W, d_minv, n_mats, out_h, out_w, warped);
     LAUNCH_CHECK(h);
     return CVB_OK;
@@ -276,6 +272,7 @@ int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, 
         attr_set = smem;
     }
     dim3 grid(n_sq, n);
+    PROF(h, "k_squares");
     k_squares<<<grid, 256, smem, h->stream>>>(a);
     LAUNCH_CHECK(h);
     return CVB_OK;

@@ -49,7 +49,11 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct ProfRec { const char *name; cudaEvent_t e0, e1; };
+
 struct cvb_handle {
+    bool profiling = false;
+    std::vector<ProfRec> prof;
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -79,6 +83,16 @@ struct cvb_state {
 };
 
 int cvb_ws(cvb_handle *h, DevBuf &b, size_t bytes, void **out);
+void cvb_prof_begin(cvb_handle *h, const char *name);
+void cvb_prof_end(cvb_handle *h);
+// bracket a kernel launch: PROF(h, "k_name"); k<<<...>>>(...); LAUNCH_CHECK(h);
+#define PROF(h, name) do { if ((h)->profiling) cvb_prof_begin((h), (name)); } while (0)
+#define LAUNCH_CHECK(h)                                  \
+    do {                                                 \
+        if ((h)->profiling) cvb_prof_end(h);             \
+        (h)->launches++;                                 \
+        CVB_CHECK_CUDA(cudaGetLastError());              \
+    } while (0)
 
 // ---- kernel launchers (cvb_enhance.cu) --------------------------------------------
 struct ClaheGeom {

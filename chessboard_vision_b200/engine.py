@@ -182,6 +182,24 @@ class Engine:
     def launch_count(self):
         return int(self.lib.cvb_launch_count(self.h))
 
+    def profile(self, on=True):
+        check(self.lib.cvb_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """-> {kernel name: (total_ms, launches)} since profile(True)."""
+        names = C.create_string_buffer(32 * 64)
+        ms = (C.c_float * 64)(); cnt = (C.c_int * 64)(); n = C.c_int()
+        check(self.lib.cvb_profile_read(self.h, names, ms, cnt, 64, C.byref(n)))
+        return {names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(): (ms[i], cnt[i]) for i in range(n.value)}
+
+    def pinned(self, shape, dtype=np.uint8):
+        """A page-locked host array (freed with the process)."""
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(self.lib.cvb_host_alloc(nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
     def empty(self, shape, dtype=np.uint8):
         return DevArray(self, shape, dtype)
 

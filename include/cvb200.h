@@ -61,6 +61,13 @@ int  cvb_synchronize(cvb_handle *h);
  * gpu_launches claim is read from here) */
 int64_t cvb_launch_count(cvb_handle *h);
 
+/* per-kernel device timing: while enabled every launch is bracketed by CUDA
+ * events on the handle's stream.  cvb_profile_read synchronises and returns,
+ * per kernel name (32 bytes each, NUL padded), the summed milliseconds and
+ * the launch count since cvb_profile_enable(h, 1).                          */
+int cvb_profile_enable(cvb_handle *h, int on);
+int cvb_profile_read(cvb_handle *h, char *names32, float *total_ms, int *counts, int max_entries, int *n_out);
+
 /* ---- device / pinned memory helpers (so hosts need no torch) --------------- */
 int cvb_malloc(cvb_handle *h, size_t bytes, void **dptr);
 int cvb_free(cvb_handle *h, void *dptr);

@@ -150,7 +150,7 @@ def gray(bgr):
 
 
 def gaussian(g, k=5):
-    assert g.dtype == np.uint8 and g.ndim == 2 and g.strides[1] == 1
+    assert g.dtype == np.uint8 and g.ndim == 2 and (g.strides[1] == 1 or g.shape[1] == 1)
     H, W = g.shape; out = np.empty((H, W), np.uint8)
     if lib().orc_gaussian(_p(g), C.c_int(H), C.c_int(W), C.c_long(g.strides[0]), C.c_int(k), _p(out)):
         raise ValueError("bad gaussian k=%r" % (k,))
