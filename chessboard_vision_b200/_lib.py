@@ -104,6 +104,7 @@ SYMBOLS = [
     ("cvb_pipeline_params_default", None, [C.POINTER(PipelineParams)]),
     ("cvb_pipeline_dev", _I, [_P, _P, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I,
                               _P, _P, _P, _P, _P, _P]),
+    ("cvb_set_chunk_frames", _I, [_P, _I]),
     ("cvb_pipeline", _I, [_P, _P, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
 ]
 

@@ -112,13 +112,17 @@ void cvb_destroy(cvb_handle *h)
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
-                      &h->ws_stats, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks};
+                      &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) {
+        cudaStreamDestroy(h->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
+    }
     prof_clear(h);
     drop_rect_cache(h);
     delete h;
@@ -686,22 +690,41 @@ int cvb_squares_dev(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW,
 }
 
 // ---- whole path ----------------------------------------------------------------------------------
-int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,
-                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select,
-                     cvb_state *state, int stream0, uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t,
-                     uint8_t *warped, cvb_square_stats *stats)
+// kernels only: matrices (inverse, device) and rectangles are already staged
+static int pipeline_launch(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,
+                           const double *d_minv, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select,
+                           cvb_state *state, int stream0, uint8_t *enhanced, uint8_t *gray, uint8_t *binary,
+                           int32_t *otsu_t, uint8_t *warped, cvb_square_stats *stats)
 {
-    REQ_H(h); REQ_IMG(n, H, W);
-    CVB_REQUIRE(bgr && p && M9 && rects, "null pointer");
-    CVB_REQUIRE(n_mats == 1 || n_mats == n, "n_mats must be 1 or n");
     const int S = p->board_size;
-    CVB_REQUIRE(S >= 8 && S <= 8192, "bad board_size %d", S);
     const size_t npx = (size_t)H * W, fb = npx * 3;
     if (!enhanced) CVB_TRY(cvb_ws(h, h->ws_enh, fb * n, (void **)&enhanced));
     if (!gray) CVB_TRY(cvb_ws(h, h->ws_gray, npx * n, (void **)&gray));
     if (!binary) CVB_TRY(cvb_ws(h, h->ws_bin, npx * n, (void **)&binary));
     if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
     if (!warped) CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * n, (void **)&warped));
+    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
+    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_minv, n_mats, S, S, warped));
+    return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
+}
+
+static int pipeline_check(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,
+                          const double *M9, int n_mats, const cvb_rect *rects)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && p && M9 && rects, "null pointer");
+    CVB_REQUIRE(n_mats == 1 || n_mats == n, "n_mats must be 1 or n");
+    CVB_REQUIRE(p->board_size >= 8 && p->board_size <= 8192, "bad board_size %d", p->board_size);
+    return CVB_OK;
+}
+
+int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,
+                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select,
+                     cvb_state *state, int stream0, uint8_t *enhanced, uint8_t *gray, uint8_t *binary, int32_t *otsu_t,
+                     uint8_t *warped, cvb_square_stats *stats)
+{
+    CVB_TRY(pipeline_check(h, bgr, n, H, W, p, M9, n_mats, rects));
+    const int S = p->board_size;
     // small host->device staging first (it synchronises), then only kernel launches
     double *d_m = nullptr;
     CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
@@ -709,30 +732,75 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, con
         cvb_rect *d_rects; int32_t *d_ofs; uint8_t *d_masks, *d_select; int max_px;
         CVB_TRY(stage_rects(h, rects, n_sq, select, S, S, &d_rects, &d_ofs, &d_masks, &d_select, &max_px));
     }
-    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
-    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_m, n_mats, S, S, warped));
-    return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
+    return pipeline_launch(h, bgr, n, H, W, p, d_m, n_mats, rects, n_sq, select, state, stream0, enhanced, gray, binary,
+                           otsu_t, warped, stats);
 }
 
+// Host-buffer variant.  The batch is cut into chunks; chunk k+1 is copied host->device on a second
+// stream while chunk k is being processed (two input buffers), so the PCIe copy and the kernels
+// overlap when the host memory is page-locked.
 int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p, const double *M9,
                  int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state, int stream0,
                  int32_t *otsu_t, cvb_square_stats *stats)
 {
-    REQ_H(h); REQ_IMG(n, H, W);
-    CVB_REQUIRE(bgr != nullptr && n_sq >= 1, "null image pointer / no squares");
+    CVB_TRY(pipeline_check(h, bgr, n, H, W, p, M9, n_mats, rects));
+    CVB_REQUIRE(n_sq >= 1, "no squares");
+    const int S = p->board_size;
     const size_t fb = (size_t)H * W * 3;
-    WS(ws_in, uint8_t, fb * n, d_in);
+    const int chunk = std::max(1, std::min(n, h->chunk_frames));
+    if (!h->copy_stream) {
+        CVB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CVB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+            CVB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    WS(ws_in, uint8_t, fb * chunk * 2, d_in);
     WS(ws_stats, cvb_square_stats, (size_t)n * n_sq, d_stats);
-    int32_t *d_otsu = nullptr;
-    CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&d_otsu));
-    CVB_CHECK_CUDA(cudaMemcpyAsync(d_in, bgr, fb * n, cudaMemcpyHostToDevice, h->stream));
-    CVB_TRY(cvb_pipeline_dev(h, d_in, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, nullptr, nullptr,
-                             nullptr, d_otsu, nullptr, d_stats));
+    WS(ws_otsu_all, int32_t, n, d_otsu);
+    double *d_m = nullptr;
+    CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
+    {
+        cvb_rect *d_rects; int32_t *d_ofs; uint8_t *d_masks, *d_select; int max_px;
+        CVB_TRY(stage_rects(h, rects, n_sq, select, S, S, &d_rects, &d_ofs, &d_masks, &d_select, &max_px));
+    }
+    // workspaces are sized here once, so no chunk triggers a synchronising reallocation
+    {
+        const size_t npx = (size_t)H * W;
+        void *t;
+        CVB_TRY(cvb_ws(h, h->ws_enh, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_gray, npx * chunk, &t));
+        CVB_TRY(cvb_ws(h, h->ws_bin, npx * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * chunk, &t));
+        CVB_TRY(cvb_ws(h, h->ws_sharp, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_blur, npx * chunk, &t));
+    }
+    // the copy stream must not start before earlier work on the compute stream that reads ws_in is done
+    CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[0], h->stream));
+    CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+    int k = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, ++k) {
+        const int cnt = std::min(chunk, n - f0), b = k & 1;
+        uint8_t *buf = d_in + (size_t)b * chunk * fb;
+        if (k >= 2) CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(buf, bgr + (size_t)f0 * fb, fb * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CVB_CHECK_CUDA(cudaEventRecord(h->ev_copy[b], h->copy_stream));
+        CVB_CHECK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
+        CVB_TRY(pipeline_launch(h, buf, cnt, H, W, p, n_mats == 1 ? d_m : d_m + (size_t)9 * f0, n_mats == 1 ? 1 : cnt, rects,
+                                n_sq, select, state, stream0 + f0, nullptr, nullptr, nullptr, d_otsu + f0, nullptr,
+                                d_stats + (size_t)f0 * n_sq));
+        CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+    }
     if (stats)
         CVB_CHECK_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(cvb_square_stats) * (size_t)n * n_sq,
                                        cudaMemcpyDeviceToHost, h->stream));
     if (otsu_t) CVB_CHECK_CUDA(cudaMemcpyAsync(otsu_t, d_otsu, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
     CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+
+int cvb_set_chunk_frames(cvb_handle *h, int frames)
+{
+    REQ_H(h);
+    CVB_REQUIRE(frames >= 1, "chunk must be >= 1 frame");
+    h->chunk_frames = frames;
     return CVB_OK;
 }
 

@@ -233,12 +233,17 @@ int launch_clahe_apply_plane(cvb_handle *h, const uint8_t *src, int n, int H, in
 //   A  stage the (optionally lighting-corrected) pixels of the tile plus halo in
 //      shared memory as packed BGRx words; out-of-image positions are filled by
 //      REFLECT_101, i.e. exactly the copyMakeBorder image bilateralFilter sees.
+//      Per-column / per-row work (mirror index, CLAHE cell and blend factors) is
+//      computed once per block.
 //   B  bilateral d=9 (bilateral_filter.dispatch.cpp / .simd.hpp): circular support
-//      r<=4 (49 taps), weight = space[k] * color[|db|+|dg|+|dr|], taps accumulated
-//      in row-major order with fmaf, result = rint(sum * (1/wsum)).  Each thread
-//      owns runs of 4 adjacent pixels; a row of the window is three LDS.128.
+//      r<=4 (49 taps), weight = f32(space[k] * color[|db|+|dg|+|dr|]) read from a
+//      shared-memory table that already holds the product for each of the 10
+//      distinct radii, taps accumulated in row-major order with fmaf,
+//      result = rint(sum * (1/wsum)).  Each thread owns runs of 4 adjacent pixels;
+//      a row of the window is three LDS.128.
 //   C  3x3 sharpen 10*c - sum9, saturate (filter2D, REFLECT_101 of the *filtered*
-//      image: mirrored neighbours index already-computed B pixels) + min/max.
+//      image: mirrored neighbours index already-computed B pixels) + min/max,
+//      then 4 pixels -> 3 words stores.
 // ---------------------------------------------------------------------------------------
 struct FusedArgs {
     const uint8_t *src;
@@ -247,9 +252,22 @@ struct FusedArgs {
     const CvbTables *tabs;
     const uint8_t *lut;       // CLAHE LUTs of all frames (LIGHT)
     ClaheGeom g;
-    const float *color;       // 768 colour weights (device)
-    float sw[81];             // spatial weights [dy+4][dx+4]
+    const float *wlut;        // [10][768] space*colour weights (device)
     int32_t *minmax;          // per frame {min,max} or null
+};
+
+// class of a tap by squared radius: 0,1,2,4,5,8,9,10,13,16 -> 0..9
+__host__ __device__ constexpr int r2_class(int r2)
+{
+    return r2 == 0 ? 0 : r2 == 1 ? 1 : r2 == 2 ? 2 : r2 == 4 ? 3 : r2 == 5 ? 4 : r2 == 8 ? 5 : r2 == 9 ? 6 : r2 == 10 ? 7
+         : r2 == 13 ? 8 : 9;
+}
+static const int kR2[10] = {0, 1, 2, 4, 5, 8, 9, 10, 13, 16};
+
+struct AxisInfo {         // one per staged column / row
+    int src;              // mirrored source coordinate
+    int o1, o2;           // CLAHE LUT offsets of the two neighbouring tiles (already * 256 [* tiles_x])
+    float a, a1;          // blend factors
 };
 
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
@@ -260,9 +278,19 @@ struct FusedCfg {
     static constexpr int AW = BW + 2 * AR, AH = BH + 2 * AR;
     static constexpr int RUNS = BW / 4;
     static_assert(TW % 4 == 0 && BW % 4 == 0 && AW % 4 == 0, "runs of 4 / LDS.128 alignment");
-    static constexpr size_t smem_bytes =
-        (size_t)AW * AH * 4 + (BIL ? (size_t)BW * BH * 4 + 768 * 4 : 0) + (LIGHT ? sizeof(SmemColorTables) : 0);
+    static constexpr size_t offA = 0;
+    static constexpr size_t offB = offA + (size_t)AW * AH * 4;
+    static constexpr size_t offW = offB + (BIL ? (size_t)BW * BH * 4 : 0);
+    static constexpr size_t offT = offW + (BIL ? 10 * 768 * 4 : 0);
+    static constexpr size_t offX = offT + (LIGHT ? sizeof(SmemColorTables) : 0);
+    static constexpr size_t smem_bytes = offX + (size_t)(AW + AH) * sizeof(AxisInfo) + (size_t)(2 * TW + 2 * TH) * 2;
 };
+
+// u8 lane k of a packed word -> float, exact: one PRMT builds 2^23 + v, one FADD removes 2^23
+CVB_DEV float byte_to_float(uint32_t q, int k)
+{
+    return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540u | (unsigned)k)) - 8388608.0f;
+}
 
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
 __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
@@ -270,11 +298,12 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *sB = BIL ? sA + AW * AH : sA;
-    float *sColor = reinterpret_cast<float *>(sB + (BIL ? BW * BH : 0));
-    SmemColorTables *sTab = reinterpret_cast<SmemColorTables *>(smem_raw + (size_t)AW * AH * 4 +
-                                                                (BIL ? (size_t)BW * BH * 4 + 768 * 4 : 0));
+    uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw + Cfg::offA);
+    uint32_t *sB = BIL ? reinterpret_cast<uint32_t *>(smem_raw + Cfg::offB) : sA;
+    const float *sW = reinterpret_cast<const float *>(smem_raw + Cfg::offW);
+    SmemColorTables *sTab = reinterpret_cast<SmemColorTables *>(smem_raw + Cfg::offT);
+    AxisInfo *sAx = reinterpret_cast<AxisInfo *>(smem_raw + Cfg::offX);          // [AW] columns then [AH] rows
+    int16_t *sNb = reinterpret_cast<int16_t *>(sAx + AW + AH);                    // xm[TW] xp[TW] ym[TH] yp[TH]
     const int tid = threadIdx.x;
     const int frame = blockIdx.z;
     const int H = a.H, W = a.W;
@@ -283,24 +312,55 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     const uint8_t *img = a.src + (size_t)frame * H * W * 3;
 
     if (LIGHT) load_color_tables(sTab, a.tabs);
-    if (BIL)
-        for (int i = tid; i < 768; i += 256) sColor[i] = __ldg(a.color + i);
-    if (LIGHT) __syncthreads();
+    if (BIL) {
+        const uint4 *gw = reinterpret_cast<const uint4 *>(a.wlut);
+        uint4 *dw = reinterpret_cast<uint4 *>(smem_raw + Cfg::offW);
+        for (int i = tid; i < 10 * 768 / 4; i += 256) dw[i] = __ldg(gw + i);
+    }
+    for (int i = tid; i < AW + AH; i += 256) {
+        AxisInfo ai;
+        const bool col = i < AW;
+        const int p = col ? reflect101(ax0 + i, W) : reflect101(ay0 + (i - AW), H);
+        ai.src = p; ai.o1 = ai.o2 = 0; ai.a = ai.a1 = 0.f;
+        if (LIGHT) {
+            const ClaheAxis ca = col ? clahe_axis(p, a.g.inv_tw, a.g.tiles_x) : clahe_axis(p, a.g.inv_th, a.g.tiles_y);
+            const int mul = col ? 256 : 256 * a.g.tiles_x;
+            ai.o1 = ca.i1 * mul; ai.o2 = ca.i2 * mul; ai.a = ca.a; ai.a1 = ca.a1;
+        }
+        sAx[i] = ai;
+    }
+    if (SHARP) {
+        for (int i = tid; i < TW; i += 256) {
+            const int X = min(x0 + i, W - 1);
+            sNb[i] = (int16_t)(reflect101(X - 1, W) - bx0);
+            sNb[TW + i] = (int16_t)(reflect101(X + 1, W) - bx0);
+        }
+        for (int i = tid; i < TH; i += 256) {
+            const int Y = min(y0 + i, H - 1);
+            sNb[2 * TW + i] = (int16_t)(reflect101(Y - 1, H) - by0);
+            sNb[2 * TW + TH + i] = (int16_t)(reflect101(Y + 1, H) - by0);
+        }
+    }
+    __syncthreads();
 
     // ---- A ----
     {
         const uint8_t *lut = LIGHT ? a.lut + (size_t)frame * a.g.tiles_x * a.g.tiles_y * 256 : nullptr;
         for (int i = tid; i < AW * AH; i += 256) {
             const int ly = i / AW, lx = i - ly * AW;
-            const int sy = reflect101(ay0 + ly, H), sx = reflect101(ax0 + lx, W);
-            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
+            const AxisInfo cx = sAx[lx], cy = sAx[AW + ly];
+            const uint8_t *p = img + ((size_t)cy.src * W + cx.src) * 3;
             const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
             uint32_t q;
             if (LIGHT) {
                 int L, A, B;
                 bgr2lab_px(sTab, c0, c1, c2, L, A, B);
-                const ClaheAxis ax = clahe_axis(sx, a.g.inv_tw, a.g.tiles_x), ay = clahe_axis(sy, a.g.inv_th, a.g.tiles_y);
-                L = clahe_interp(lut, a.g.tiles_x, ax, ay, L);
+                const uint8_t *l1 = lut + cy.o1 + L, *l2 = lut + cy.o2 + L;
+                const float l11 = (float)__ldg(l1 + cx.o1), l12 = (float)__ldg(l1 + cx.o2);
+                const float l21 = (float)__ldg(l2 + cx.o1), l22 = (float)__ldg(l2 + cx.o2);
+                const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, cx.a1), __fmul_rn(l12, cx.a)), cy.a1);
+                const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, cx.a1), __fmul_rn(l22, cx.a)), cy.a);
+                L = round_u8(__fadd_rn(top, bot));
                 q = lab2bgr_px(sTab, L, A, B);
             } else {
                 q = pack_bgr(c0, c1, c2);
@@ -329,7 +389,7 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
                 const uint32_t *rowp = sA + (row + 4 + dy) * AW + r4;
                 uint32_t px[12];
                 float fb[12], fg[12], fr[12];
-                // columns r4 .. r4+11 of the A tile hold image x = X-4 .. X+7
+                // columns r4 .. r4+11 of the A tile hold image x = X-4 .. X+7;
                 // first needed column: 4 - (largest |dx| on this row of the disc)
                 const int ady = dy < 0 ? -dy : dy;
                 const int lo = ady == 4 ? 4 : ady == 3 ? 2 : ady >= 1 ? 1 : 0;
@@ -342,9 +402,9 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
 #pragma unroll
                 for (int c = 0; c < 12; ++c) {
                     if (c < lo || c > 11 - lo) continue;
-                    fb[c] = (float)(px[c] & 0xffu);
-                    fg[c] = (float)((px[c] >> 8) & 0xffu);
-                    fr[c] = (float)((px[c] >> 16) & 0xffu);
+                    fb[c] = byte_to_float(px[c], 0);
+                    fg[c] = byte_to_float(px[c], 1);
+                    fr[c] = byte_to_float(px[c], 2);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -352,7 +412,7 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
                     for (int dx = -4; dx <= 4; ++dx) {
                         if (dy * dy + dx * dx > 16) continue;
                         const int c = j + 4 + dx;
-                        const float w = __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sColor[__vsadu4(px[c], ctr[j])]);
+                        const float w = sW[r2_class(dy * dy + dx * dx) * 768 + __vsadu4(px[c], ctr[j])];
                         wsum[j] = __fadd_rn(wsum[j], w);
                         sb[j] = __fmaf_rn(fb[c], w, sb[j]);
                         sg[j] = __fmaf_rn(fg[c], w, sg[j]);
@@ -373,8 +433,54 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
         __syncthreads();
     }
 
-    // ---- C ----
+    // ---- C ----  (results of the tile go to sOut = the start of sA, free once B is done)
+    uint32_t *sOut = sA;
     int vmin = 255, vmax = 0;
+    uint32_t keep[(TW * TH + 255) / 256];
+#pragma unroll
+    for (int it = 0; it < (TW * TH + 255) / 256; ++it) {
+        const int i = tid + it * 256;
+        uint32_t q = 0;
+        if (i < TW * TH) {
+            const int ty = i / TW, tx = i - ty * TW;
+            if (y0 + ty < H && x0 + tx < W) {
+                if (SHARP) {
+                    const int xm = sNb[tx], xp = sNb[TW + tx], xc = tx + Cfg::BX;
+                    const int ym = sNb[2 * TW + ty], yp = sNb[2 * TW + TH + ty], yc = ty + Cfg::BY;
+                    const uint32_t *r0 = sB + ym * BW, *r1 = sB + yc * BW, *r2 = sB + yp * BW;
+                    const uint32_t c = r1[xc];
+                    const uint32_t t0 = r0[xm], t1 = r0[xc], t2 = r0[xp], t3 = r1[xm], t5 = r1[xp], t6 = r2[xm], t7 = r2[xc],
+                                   t8 = r2[xp];
+                    // 16-bit lanes: (b, r) in one word, g in the other; nine bytes sum to <= 2295
+                    const uint32_t s02 = (t0 & 0x00ff00ffu) + (t1 & 0x00ff00ffu) + (t2 & 0x00ff00ffu) + (t3 & 0x00ff00ffu) +
+                                         (c & 0x00ff00ffu) + (t5 & 0x00ff00ffu) + (t6 & 0x00ff00ffu) + (t7 & 0x00ff00ffu) +
+                                         (t8 & 0x00ff00ffu);
+                    const uint32_t s1 = ((t0 >> 8) & 0xffu) + ((t1 >> 8) & 0xffu) + ((t2 >> 8) & 0xffu) + ((t3 >> 8) & 0xffu) +
+                                        ((c >> 8) & 0xffu) + ((t5 >> 8) & 0xffu) + ((t6 >> 8) & 0xffu) + ((t7 >> 8) & 0xffu) +
+                                        ((t8 >> 8) & 0xffu);
+                    const int b = clamp_u8(10 * (int)(c & 0xff) - (int)(s02 & 0xffff));
+                    const int g = clamp_u8(10 * (int)((c >> 8) & 0xff) - (int)s1);
+                    const int r = clamp_u8(10 * (int)((c >> 16) & 0xff) - (int)(s02 >> 16));
+                    q = pack_bgr(b, g, r);
+                } else {
+                    q = sB[(ty + Cfg::BY) * BW + tx + Cfg::BX];
+                }
+                if (a.minmax) {
+                    const int b = q & 0xff, g = (q >> 8) & 0xff, r = (q >> 16) & 0xff;
+                    vmin = min(vmin, min(b, min(g, r)));
+                    vmax = max(vmax, max(b, max(g, r)));
+                }
+            }
+        }
+        keep[it] = q;
+    }
+    __syncthreads();                      // every read of sB (may alias sA) is done
+#pragma unroll
+    for (int it = 0; it < (TW * TH + 255) / 256; ++it) {
+        const int i = tid + it * 256;
+        if (i < TW * TH) sOut[i] = keep[it];
+    }
+    __syncthreads();
     uint8_t *out = a.dst + (size_t)frame * H * W * 3;
     const bool fast = (W % 4 == 0) && (x0 + TW <= W) && ((reinterpret_cast<uintptr_t>(a.dst) & 3) == 0);
     constexpr int GROUPS = TW / 4;
@@ -382,39 +488,8 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
         const int ty = item / GROUPS, tx4 = (item - ty * GROUPS) * 4;
         const int Y = y0 + ty;
         if (Y >= H) break;
-        uint32_t res[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int X = x0 + tx4 + j;
-            uint32_t q = 0;
-            if (X < W) {
-                if (SHARP) {
-                    const int ym = reflect101(Y - 1, H) - by0, yc = Y - by0, yp = reflect101(Y + 1, H) - by0;
-                    const int xm = reflect101(X - 1, W) - bx0, xc = X - bx0, xp = reflect101(X + 1, W) - bx0;
-                    uint32_t s02 = 0, s1 = 0;   // 16-bit lanes: (b, r) and (g)
-                    const int ys[3] = {ym, yc, yp}, xs[3] = {xm, xc, xp};
-#pragma unroll
-                    for (int u = 0; u < 3; ++u)
-#pragma unroll
-                        for (int v = 0; v < 3; ++v) {
-                            const uint32_t t = sB[ys[u] * BW + xs[v]];
-                            s02 += t & 0x00ff00ffu;
-                            s1 += (t >> 8) & 0xffu;
-                        }
-                    const uint32_t c = sB[yc * BW + xc];
-                    const int b = clamp_u8(10 * (int)(c & 0xff) - (int)(s02 & 0xffff));
-                    const int g = clamp_u8(10 * (int)((c >> 8) & 0xff) - (int)s1);
-                    const int r = clamp_u8(10 * (int)((c >> 16) & 0xff) - (int)(s02 >> 16));
-                    q = pack_bgr(b, g, r);
-                } else {
-                    q = sB[(Y - by0) * BW + (X - bx0)];
-                }
-                const int b = q & 0xff, g = (q >> 8) & 0xff, r = (q >> 16) & 0xff;
-                vmin = min(vmin, min(b, min(g, r)));
-                vmax = max(vmax, max(b, max(g, r)));
-            }
-            res[j] = q;
-        }
+        const uint4 rq = *reinterpret_cast<const uint4 *>(sOut + ty * TW + tx4);
+        const uint32_t res[4] = {rq.x, rq.y, rq.z, rq.w};
         uint8_t *o = out + ((size_t)Y * W + x0 + tx4) * 3;
         if (fast) {
             // 4 pixels = 12 bytes = 3 aligned words
@@ -462,21 +537,29 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
 {
     FusedArgs a;
     a.src = src; a.dst = out; a.H = H; a.W = W; a.tabs = h->d_tables; a.lut = lut; a.minmax = minmax;
-    a.color = nullptr;
+    a.wlut = nullptr;
     if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
-    memset(a.sw, 0, sizeof a.sw);
     if (bilateral) {
-        if (h->color_sigma != sigma_color || !h->d_color) {
-            float color[768];
-            cvb_host_bilateral_tables(sigma_color, sigma_space, color, nullptr);
-            if (!h->d_color) CVB_CHECK_CUDA(cudaMalloc(&h->d_color, sizeof color));
-            // pageable source: the copy is staged before the call returns
-            CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, color, sizeof color, cudaMemcpyHostToDevice, h->stream));
-            CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
-            h->color_sigma = sigma_color;
+        if (h->color_sigma != sigma_color || h->space_sigma != sigma_space || !h->d_color) {
+            std::vector<float> color(768), space(81), wl(10 * 768);
+            cvb_host_bilateral_tables(sigma_color, sigma_space, color.data(), space.data());
+            for (int c = 0; c < 10; ++c) {
+                // any tap of that radius (weights depend on dy^2+dx^2 only)
+                float sw = 0.f;
+                for (int dy = -4; dy <= 4; ++dy)
+                    for (int dx = -4; dx <= 4; ++dx)
+                        if (dy * dy + dx * dx == kR2[c]) sw = space[(dy + 4) * 9 + dx + 4];
+                for (int i = 0; i < 768; ++i) {
+                    volatile float prod = sw * color[i];      // one f32 rounding, as space_weight[k]*color_weight[i]
+                    wl[c * 768 + i] = prod;
+                }
+            }
+            if (!h->d_color) CVB_CHECK_CUDA(cudaMalloc(&h->d_color, wl.size() * sizeof(float)));
+            CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // pageable source dies at scope end
+            h->color_sigma = sigma_color; h->space_sigma = sigma_space;
         }
-        cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
-        a.color = h->d_color;
+        a.wlut = h->d_color;
     }
     constexpr int TW = 60, TH = 30;
     if (light && bilateral && sharpen) return launch_fused_t<TW, TH, true, true, true>(h, a, n);
@@ -638,9 +721,13 @@ int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 128x16, halo 2.
-// Rows are staged through shared memory with 16-byte transfers on both the
-// read (sharpened frame) and the write (enhanced frame) side.
+// Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 128x32, halo 2.
+//   1  rows of the sharpened frame (tile + 4 columns each side, clipped to the image)
+//      are staged in shared memory with 16-byte transfers;
+//   2  groups of 4 pixels: min-max map (skipped when it is the identity), write the
+//      enhanced pixels (3 words), gray (1 word) and keep gray in shared memory;
+//   3  horizontal [1 4 6 4 1]; 4  vertical [1 4 6 4 1], (sum+128)>>8, histogram.
+// Mirror columns / rows (REFLECT_101 of GaussianBlur) are taken from the staged rows.
 // ---------------------------------------------------------------------------------------
 template <bool NORM>
 __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src, int H, int W,
@@ -648,110 +735,165 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                                                 uint8_t *__restrict__ gray, uint8_t *__restrict__ blurred,
                                                 int32_t *__restrict__ hist)
 {
-    constexpr int FW = 128, FH = 16, R = 2, GW = FW + 2 * R, GH = FH + 2 * R;
-    constexpr int ROWB = GW * 3 + 16 + 12;               // staged bytes per row (+phase, padded to 16)
-    constexpr int ROWP = (ROWB + 15) / 16 * 16;
-    __shared__ __align__(16) uint8_t s_row[GH][ROWP];     // raw BGR rows (normalized in place for interior rows)
-    __shared__ __align__(16) uint8_t s_g[GH][GW + 12];    // gray with halo
-    __shared__ uint16_t s_h[GH][FW];                      // horizontal pass
+    constexpr int FW = 128, FH = 32, R = 2, PADX = 4;
+    constexpr int GH = FH + 2 * R;                 // staged rows
+    constexpr int SW = FW + 2 * PADX;              // staged / gray columns: X = x0-4 .. x0+131
+    constexpr int ROWP = (SW * 3 + 15 + 15) / 16 * 16;
+    constexpr int VPR = ROWP / 16;                 // vector slots per staged row
+    __shared__ __align__(16) uint8_t s_raw[GH][ROWP];
+    __shared__ __align__(16) uint8_t s_g[GH][SW];
+    __shared__ __align__(8) uint16_t s_h[GH][FW];
     __shared__ int s_hist[8][256];
     __shared__ uint8_t s_map[256];
     const int tid = threadIdx.x, frame = blockIdx.z;
     const int x0 = blockIdx.x * FW, y0 = blockIdx.y * FH;
     const size_t fo = (size_t)frame * H * W;
     const uint8_t *img = src + fo * 3;
-    for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
-    if (NORM) s_map[tid] = (uint8_t)normalize_value(tid, minmax[2 * frame], minmax[2 * frame + 1]);
-    // columns actually present in the image for this tile (+halo)
-    const int cx0 = max(x0 - R, 0), cx1 = min(x0 + FW + R, W);
-    const int span = (cx1 - cx0) * 3;
-    for (int ly = 0; ly < GH; ++ly) {
-        const int sy = reflect101(y0 - R + ly, H);
-        g2s_span(s_row[ly], img + ((size_t)sy * W + cx0) * 3, span, tid, 256);
-    }
-    __syncthreads();
-    // normalize in shared memory (bytes), then emit the enhanced rows of the interior
+    if (hist)
+        for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
+    bool identity = true;
     if (NORM) {
-        for (int ly = 0; ly < GH; ++ly) {
-            const int sy = reflect101(y0 - R + ly, H);
-            const int ph = span_phase(img + ((size_t)sy * W + cx0) * 3);
-            for (int i = tid; i < span; i += 256) s_row[ly][ph + i] = s_map[s_row[ly][ph + i]];
-        }
-        __syncthreads();
+        const int lo = minmax[2 * frame], hi = minmax[2 * frame + 1];
+        identity = (lo == 0 && hi == 255);
+        if (!identity) s_map[tid] = (uint8_t)normalize_value(tid, lo, hi);
     }
-    if (enhanced) {
-        const int ix0 = x0, ix1 = min(x0 + FW, W);
-        for (int ly = R; ly < GH - R; ++ly) {
-            const int Y = y0 - R + ly;
-            if (Y >= H) break;
-            // same row of the same frame layout => same phase for source and destination
-            // only when src and dst bases agree modulo 16; handle generally via a byte loop otherwise
-            const uint8_t *srow = img + ((size_t)Y * W + cx0) * 3;
-            uint8_t *drow = enhanced + fo * 3 + ((size_t)Y * W + ix0) * 3;
-            const int ph = span_phase(srow);
-            const uint8_t *sp = s_row[ly] + ph + (ix0 - cx0) * 3;
-            const int nb = (ix1 - ix0) * 3;
-            if (((reinterpret_cast<uintptr_t>(sp) ^ reinterpret_cast<uintptr_t>(drow)) & 15) == 0) {
-                // aligned-compatible: reuse the span copier with the implied base
-                s2g_span(drow, sp - span_phase(drow), nb, tid, 256);
-            } else {
-                for (int i = tid; i < nb; i += 256) drow[i] = sp[i];
-            }
+    const int cx0 = max(x0 - PADX, 0), cx1 = min(x0 + FW + PADX, W);
+    const int span = (cx1 - cx0) * 3;
+    // ---- 1: stage rows; one (row, 16-byte slot) item per thread step ----
+    for (int item = tid; item < GH * VPR; item += 256) {
+        const int ly = item / VPR, v = item - ly * VPR;
+        const uint8_t *g = img + ((size_t)reflect101(y0 - R + ly, H) * W + cx0) * 3;
+        uint8_t *s = s_raw[ly];
+        const int phase = span_phase(g);
+        const int head = min(span, (16 - phase) & 15);
+        const int body = (span - head) >> 4;
+        if (v < body) {
+            reinterpret_cast<uint4 *>(s + phase + head)[v] = __ldg(reinterpret_cast<const uint4 *>(g + head) + v);
+        } else if (v == VPR - 1) {
+            for (int i = 0; i < head; ++i) s[phase + i] = __ldg(g + i);
+        } else if (v == VPR - 2) {
+            for (int i = head + (body << 4); i < span; ++i) s[phase + i] = __ldg(g + i);
         }
-    }
-    // gray of every staged position (mirror columns map into the staged span)
-    for (int i = tid; i < GH * GW; i += 256) {
-        const int ly = i / GW, lx = i - ly * GW;
-        if (x0 - R + lx >= W + R) continue;   // beyond any mirrored column a valid output can need
-        const int sy = reflect101(y0 - R + ly, H);
-        const int sx = reflect101(x0 - R + lx, W);
-        const int ph = span_phase(img + ((size_t)sy * W + cx0) * 3);
-        const uint8_t *p = s_row[ly] + ph + (sx - cx0) * 3;
-        const int gv = gray_px(p[0], p[1], p[2]);
-        s_g[ly][lx] = (uint8_t)gv;
     }
     __syncthreads();
-    if (gray) {
-        for (int i = tid; i < FH * (FW / 4); i += 256) {
-            const int ly = i / (FW / 4), lx = (i - ly * (FW / 4)) * 4;
-            const int Y = y0 + ly, X = x0 + lx;
-            if (Y >= H || X >= W) continue;
-            uint8_t *o = gray + fo + (size_t)Y * W + X;
-            const uint8_t *s = &s_g[ly + R][lx + R];
-            if (X + 3 < W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-                *reinterpret_cast<uint32_t *>(o) = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24);
+    // ---- 2: map, emit enhanced + gray, keep gray ----
+    constexpr int NG = SW / 4;                      // 34 groups per row, group gi covers X = x0-4+4gi ..
+    const bool al4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int item = tid; item < GH * NG; item += 256) {
+        const int ly = item / NG, gi = item - ly * NG;
+        const int Y = y0 - R + ly;
+        const int sy = reflect101(Y, H);
+        const int X = x0 - PADX + 4 * gi;
+        const uint8_t *rowg = img + ((size_t)sy * W + cx0) * 3;
+        const uint8_t *s = s_raw[ly] + span_phase(rowg);
+        uint32_t gpack = 0;
+        if (X >= 0 && X + 3 < W) {
+            const uint8_t *p = s + (X - cx0) * 3;
+            uint32_t w0, w1, w2;
+            if (al4) {   // (row start + X*3) is a multiple of 4 when W%4==0, X%4==0 and the frame base is aligned
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(p);
+                w0 = p32[0]; w1 = p32[1]; w2 = p32[2];
             } else {
-                for (int j = 0; j < 4 && X + j < W; ++j) o[j] = s[j];
+                w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+                w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
+                w2 = p[8] | (p[9] << 8) | (p[10] << 16) | ((uint32_t)p[11] << 24);
             }
-        }
-    }
-    // blur 5x5: [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8
-    for (int i = tid; i < GH * FW; i += 256) {
-        const int ly = i / FW, lx = i - ly * FW;
-        const uint8_t *s = &s_g[ly][lx];
-        s_h[ly][lx] = (uint16_t)(s[0] + 4 * s[1] + 6 * s[2] + 4 * s[3] + s[4]);
-    }
-    __syncthreads();
-    int *myh = s_hist[tid >> 5];
-    for (int i = tid; i < FH * (FW / 4); i += 256) {
-        const int ly = i / (FW / 4), lx = (i - ly * (FW / 4)) * 4;
-        const int Y = y0 + ly, X = x0 + lx;
-        if (Y >= H || X >= W) continue;
-        uint32_t packed = 0;
+            if (NORM && !identity) {
+                w0 = s_map[w0 & 0xff] | (s_map[(w0 >> 8) & 0xff] << 8) | (s_map[(w0 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w0 >> 24] << 24);
+                w1 = s_map[w1 & 0xff] | (s_map[(w1 >> 8) & 0xff] << 8) | (s_map[(w1 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w1 >> 24] << 24);
+                w2 = s_map[w2 & 0xff] | (s_map[(w2 >> 8) & 0xff] << 8) | (s_map[(w2 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w2 >> 24] << 24);
+            }
+            // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+            const int g0 = gray_px(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+            const int g1 = gray_px(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+            const int g2 = gray_px((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+            const int g3 = gray_px((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+            gpack = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+            if (ly >= R && ly < GH - R && Y < H && gi >= 1 && gi <= FW / 4) {   // interior of this tile
+                const size_t po = (size_t)Y * W + X;
+                if (enhanced) {
+                    uint8_t *o = enhanced + (fo + po) * 3;
+                    if (al4 && (reinterpret_cast<uintptr_t>(enhanced) & 3) == 0) {
+                        uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+                        o32[0] = w0; o32[1] = w1; o32[2] = w2;
+                    } else {
+                        const uint32_t ww[3] = {w0, w1, w2};
+                        for (int i = 0; i < 12; ++i) o[i] = (uint8_t)(ww[i >> 2] >> (8 * (i & 3)));
+                    }
+                }
+                if (gray) {
+                    uint8_t *o = gray + fo + po;
+                    if (al4 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0) *reinterpret_cast<uint32_t *>(o) = gpack;
+                    else
+                        for (int i = 0; i < 4; ++i) o[i] = (uint8_t)(gpack >> (8 * i));
+                }
+            }
+        } else {
+            // group touching an image edge: per pixel, mirror columns come from the staged span
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = (s_h[ly][lx + j] + 4 * s_h[ly + 1][lx + j] + 6 * s_h[ly + 2][lx + j] + 4 * s_h[ly + 3][lx + j] +
-                           s_h[ly + 4][lx + j] + 128) >> 8;
-            if (X + j < W) {
-                packed |= (uint32_t)v << (8 * j);
-                if (hist) atomicAdd(&myh[v], 1);
+            for (int j = 0; j < 4; ++j) {
+                const int Xj = X + j;
+                if (Xj < x0 - R || Xj >= x0 + FW + R || Xj >= W + R) continue;   // never read by a valid output
+                const int sx = reflect101(Xj, W);
+                const uint8_t *p = s + (sx - cx0) * 3;
+                int b = p[0], g = p[1], r = p[2];
+                if (NORM && !identity) { b = s_map[b]; g = s_map[g]; r = s_map[r]; }
+                const int gv = gray_px(b, g, r);
+                gpack |= (uint32_t)gv << (8 * j);
+                if (Xj >= x0 && Xj < W && Xj < x0 + FW && ly >= R && ly < GH - R && Y < H) {
+                    const size_t po = (size_t)Y * W + Xj;
+                    if (enhanced) {
+                        uint8_t *o = enhanced + (fo + po) * 3;
+                        o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+                    }
+                    if (gray) gray[fo + po] = (uint8_t)gv;
+                }
             }
         }
+        *reinterpret_cast<uint32_t *>(&s_g[ly][4 * gi]) = gpack;
+    }
+    __syncthreads();
+    // ---- 3: horizontal pass, 4 outputs per item (output x <-> gray columns x+2 .. x+6) ----
+    for (int item = tid; item < GH * (FW / 4); item += 256) {
+        const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
+        const uint32_t *gp = reinterpret_cast<const uint32_t *>(&s_g[ly][x]);
+        const uint32_t a = gp[0], b = gp[1], c = gp[2];          // columns x .. x+11
+        const int v2 = (a >> 16) & 0xff, v3 = a >> 24, v4 = b & 0xff, v5 = (b >> 8) & 0xff, v6 = (b >> 16) & 0xff,
+                  v7 = b >> 24, v8 = c & 0xff, v9 = (c >> 8) & 0xff;
+        const uint32_t h0 = v2 + 4 * v3 + 6 * v4 + 4 * v5 + v6, h1 = v3 + 4 * v4 + 6 * v5 + 4 * v6 + v7;
+        const uint32_t h2 = v4 + 4 * v5 + 6 * v6 + 4 * v7 + v8, h3 = v5 + 4 * v6 + 6 * v7 + 4 * v8 + v9;
+        *reinterpret_cast<uint2 *>(&s_h[ly][x]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    }
+    __syncthreads();
+    // ---- 4: vertical pass + histogram ----
+    int *myh = s_hist[tid >> 5];
+    for (int item = tid; item < FH * (FW / 4); item += 256) {
+        const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
+        const int Y = y0 + ly, X = x0 + x;
+        if (Y >= H || X >= W) continue;
+        uint32_t lo = 0, hi = 0;      // 16-bit lanes: outputs (0,1) and (2,3); sums <= 255*256 fit
+        {
+            const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
+            const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
+            const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
+            const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
+            const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
+            // per-lane sums stay below 2^16 (max 255*256 = 65280) so no carry crosses lanes
+            lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
+            hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
+        }
+        const int o0 = ((lo & 0xffff) + 128) >> 8, o1 = ((lo >> 16) + 128) >> 8;
+        const int o2 = ((hi & 0xffff) + 128) >> 8, o3 = ((hi >> 16) + 128) >> 8;
+        const int ov[4] = {o0, o1, o2, o3};
+        const int nvalid = min(4, W - X);
+        if (hist)
+            for (int j = 0; j < nvalid; ++j) atomicAdd(&myh[ov[j]], 1);
         if (blurred) {
             uint8_t *o = blurred + fo + (size_t)Y * W + X;
-            if (X + 3 < W && (reinterpret_cast<uintptr_t>(o) & 3) == 0) *reinterpret_cast<uint32_t *>(o) = packed;
+            if (nvalid == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0)
+                *reinterpret_cast<uint32_t *>(o) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
             else
-                for (int j = 0; j < 4 && X + j < W; ++j) o[j] = (uint8_t)(packed >> (8 * j));
+                for (int j = 0; j < nvalid; ++j) o[j] = (uint8_t)ov[j];
         }
     }
     if (hist) {
@@ -766,7 +908,7 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
                   uint8_t *gray, uint8_t *blurred, int32_t *hist)
 {
     if (hist) CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * (size_t)n, h->stream));
-    dim3 grid((W + 127) / 128, (H + 15) / 16, n);
+    dim3 grid((W + 127) / 128, (H + 31) / 32, n);
     PROF(h, "k_finish");
     if (minmax) k_finish<true><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
     else k_finish<false><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);

@@ -62,10 +62,14 @@ struct cvb_handle {
     CvbTables *d_tables = nullptr;
     // bilateral colour LUT cache (device) keyed by sigma_color
     float *d_color = nullptr;
-    double color_sigma = -1.0;
+    double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
     DevBuf ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
-    DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_stats, ws_rects, ws_select, ws_mats;
+    DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
+    // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int chunk_frames = 16;
     // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
     DevBuf ws_masks;
     void *pinned = nullptr;

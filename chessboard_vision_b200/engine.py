@@ -182,6 +182,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.cvb_launch_count(self.h))
 
+    def set_chunk_frames(self, frames):
+        """Frames per chunk of the host-buffer pipeline (copy/compute overlap granularity)."""
+        check(self.lib.cvb_set_chunk_frames(self.h, int(frames)))
+
     def profile(self, on=True):
         check(self.lib.cvb_profile_enable(self.h, int(bool(on))))
 
