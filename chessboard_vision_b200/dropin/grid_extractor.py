@@ -1,0 +1,52 @@
+"""Drop-in for the reference's grid_extractor module (grid_extractor.py:1-163).
+
+split_board keeps the reference contract exactly: a dict keyed (file, rank)
+in r-major insertion order (rank 8 first) whose values are ndarray VIEWS into
+the warped image.  The drop-in ChangeDetector / PieceDetector recognise such
+views (one common parent array) and hand the parent plus the rectangles to the
+batched square kernel without repacking.
+"""
+from chessboard_vision_b200.engine import grid_rects
+from chessboard_vision_b200.hostapi import load_reference_module
+
+
+def _split(img_warped, rects, keys):
+    return {k: img_warped[y:y + h, x:x + w] for k, (x, y, w, h) in zip(keys, rects)}
+
+
+class GridExtractor:
+    def __init__(self):
+        pass
+
+    def split_board(self, img_warped):
+        """grid_extractor.py:8-58: 64 equal squares of (rows//8, cols//8)."""
+        rows, cols = img_warped.shape[0], img_warped.shape[1]
+        if img_warped.ndim != 3:
+            raise ValueError("not enough values to unpack (expected 3, got %d)" % img_warped.ndim)
+        rects, keys = grid_rects((rows, cols))
+        return _split(img_warped, rects, keys)
+
+
+class SmartGridExtractor:
+    def __init__(self, debug=False):
+        self.grid_lines_x = None
+        self.grid_lines_y = None
+        self.debug = debug
+
+    def refine_grid(self, img_warped):
+        """grid_extractor.py:66-121 (Canny + projection peaks): calibration-time code outside the hot
+        path; run by the reference's own implementation."""
+        ref = load_reference_module("grid_extractor")
+        if ref is None:
+            raise NotImplementedError("refine_grid is outside the B200 hot path and the reference's "
+                                      "grid_extractor.py was not found on sys.path")
+        helper = ref.SmartGridExtractor(debug=self.debug)
+        self.grid_lines_x, self.grid_lines_y = helper.refine_grid(img_warped)
+        return self.grid_lines_x, self.grid_lines_y
+
+    def split_board(self, img_warped):
+        """grid_extractor.py:123-163: calibrated grid lines, linear fallback when unset."""
+        if self.grid_lines_x is None or self.grid_lines_y is None:
+            return GridExtractor().split_board(img_warped)
+        rects, keys = grid_rects(None, self.grid_lines_x, self.grid_lines_y)
+        return _split(img_warped, rects, keys)

@@ -1,0 +1,46 @@
+"""Multi-GPU layout of the hot path: frames / camera streams are independent units, so they are
+sharded across ranks (one process per GPU) with NO data-path collective.  The only
+cross-rank traffic is control plane: a barrier, the max-over-ranks of the timed region, and an
+optional gather of the small per-square result records to rank 0.
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block of `n_items` owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(int(n_items), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def stream_owner(stream_id, world):
+    """Camera stream -> rank that keeps its ChangeDetector / PieceDetector state (stream mode)."""
+    return int(stream_id) % int(world)
+
+
+def dist_max(value):
+    """max over ranks of a python float (the time of the slowest rank); identity without a group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_records(local, dst=0):
+    """Gather per-rank structured result arrays (n_local, n_sq) on `dst`, in rank order (= shard order
+    of shard_range).  Returns the concatenated array on dst, None elsewhere."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    bucket = [None] * world if rank == dst else None
+    dist.gather_object((local.dtype.descr, local.shape, local.tobytes()), bucket, dst=dst)
+    if rank != dst:
+        return None
+    parts = [np.frombuffer(b, dtype=np.dtype([tuple(d) if isinstance(d, list) else d for d in descr])).reshape(shape)
+             for descr, shape, b in bucket]
+    return np.concatenate(parts, axis=0)

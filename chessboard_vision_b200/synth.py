@@ -44,3 +44,19 @@ def change_pair(frame, squares, value=255, board_pts=None):
     for (x, y, w, h) in squares:
         out[y:y + h, x:x + w] = value
     return out
+
+
+def board_with_pieces(seed=11, base_seed=7, size=620):
+    """A warped-board-like image (board_frame) with 20 random coloured discs near square centres."""
+    rng = np.random.default_rng(seed)
+    board = board_frame(size, size, base_seed)
+    out = board.copy()
+    yy, xx = np.ogrid[:size, :size]
+    sq = size // 8
+    for _ in range(20):
+        c, r = int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        cx, cy = c * sq + sq // 2 + int(rng.integers(-4, 5)), r * sq + sq // 2 + int(rng.integers(-4, 5))
+        rad = int(rng.integers(18, 30))
+        col = rng.integers(0, 256, 3)
+        out[((xx - cx) ** 2 + (yy - cy) ** 2) <= rad * rad] = col
+    return board, out

@@ -1,0 +1,140 @@
+"""A numpy/oracle-backed stand-in for chessboard_vision_b200.engine.Engine, used ONLY by the CPU
+tests to exercise the host logic of the drop-in modules (dict handling, state windows, gating)
+where no GPU exists.  Every numeric result comes from the CPU oracle."""
+import numpy as np
+
+import oracle as O
+from chessboard_vision_b200 import _lib
+from chessboard_vision_b200.engine import STATS_DTYPE
+from chessboard_vision_b200._lib import SquareParams, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE
+
+
+class FakeState:
+    def __init__(self, n, BH, BW):
+        self.n_streams, self.BH, self.BW = n, BH, BW
+        self.planes = {_lib.PLANE_PD_REF: np.zeros((n, BH, BW), np.uint8), _lib.PLANE_PD_CUR: np.zeros((n, BH, BW), np.uint8),
+                       _lib.PLANE_FLAGS: np.zeros((n, BH, BW), np.uint8),
+                       _lib.PLANE_CD_MEAN: np.zeros((n, BH, BW), np.float32), _lib.PLANE_CD_VAR: np.zeros((n, BH, BW), np.float32)}
+        self.ptr = 1
+
+    def get(self, stream, plane):
+        return self.planes[plane][stream].copy()
+
+    def set(self, stream, plane, arr):
+        self.planes[plane][stream] = arr
+
+    def reset(self, stream=-1):
+        self.planes[_lib.PLANE_FLAGS][...] = 0
+
+    def free(self):
+        self.ptr = None
+
+
+class FakeEngine:
+    h = 1
+    launches = 0
+
+    def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0):
+        return dict(clip=clip, tiles=tiles)
+
+    def clahe(self, plane, clip=3.0, tiles=(8, 8), return_tables=False):
+        return O.clahe(plane, clip, tiles, return_tables)
+
+    def correct_lighting(self, img, clip=3.0, tiles=(8, 8)):
+        return O.correct_lighting(img, clip, tiles)
+
+    def bilateral(self, img, d=9, sc=75.0, ss=75.0):
+        return O.bilateral(img, d, sc, ss, True)
+
+    def sharpen(self, img):
+        return O.sharpen(img)
+
+    def normalize(self, img):
+        return O.normalize(img, True)
+
+    def gray(self, img):
+        return O.gray(img)
+
+    def gaussian(self, g, k=5):
+        return O.gaussian(g, k)
+
+    def prepare_analysis(self, img):
+        return O.prepare_analysis(img)
+
+    def process_pipeline(self, img, params=None):
+        return O.process_pipeline(img, True)
+
+    def enhance(self, img, params=None):
+        enh = O.process_pipeline(img, True)
+        g, b, t, _ = O.prepare_analysis(enh, True)
+        return enh, g, b, t
+
+    def get_perspective_transform(self, s, d):
+        return O.get_perspective(s, d)
+
+    def warp(self, img, M, size):
+        return O.warp(img, M, size)
+
+    def square_params(self, ops=SQ_PD_STATS, pd_blur=5, cd_blur=5, z_threshold=2.5, alpha=0.1, initial_variance=100.0,
+                      min_variance=10.0):
+        p = SquareParams()
+        p.ops, p.pd_blur, p.cd_blur = int(ops), int(pd_blur), int(cd_blur)
+        p.z_threshold = np.float32(z_threshold); p.alpha = np.float32(alpha); p.one_minus_alpha = np.float32(1 - alpha)
+        p.initial_variance = np.float32(initial_variance); p.min_variance = np.float32(min_variance)
+        return p
+
+    def new_state(self, n, BH, BW):
+        return FakeState(n, BH, BW)
+
+    def squares(self, boards, rects, p, state=None, stream0=0, select=None, want_stats=True):
+        FakeEngine.launches += 1
+        b = np.asarray(boards)
+        if b.ndim == 2 or (b.ndim == 3 and b.shape[-1] == 3):
+            b = b[None]
+        out = np.zeros((b.shape[0], len(rects)), STATS_DTYPE)
+        for f in range(b.shape[0]):
+            s = stream0 + f
+            for i, (x, y, w, h) in enumerate(rects):
+                sel = True if select is None else bool(select[i])
+                sq = b[f, y:y + h, x:x + w]
+                st = out[f, i]
+                st["n"] = w * h
+                fl = state.planes[_lib.PLANE_FLAGS][s, y, x] if state is not None else 0
+                if p.ops & (SQ_PD_STATS | SQ_PD_SET_REF):
+                    g = O.square_preprocess(sq, p.pd_blur)
+                    if p.ops & SQ_PD_STATS:
+                        ref = state.planes[_lib.PLANE_PD_REF][s, y:y + h, x:x + w] if (fl & 1) else None
+                        o = O.pd_square_stats(g, ref)
+                        st["has_ref"] = 1 if ref is not None else 0
+                        st["sum"], st["sumsq"], st["sad"] = o["sum"], o["sumsq"], max(o["sad"], 0)
+                        st["center_sum"], st["center_cnt"] = o["center_sum"], o["center_cnt"]
+                        st["border_sum"], st["border_cnt"] = o["border_sum"], o["border_cnt"]
+                        st["ring_sum"], st["ring_cnt"] = o["ring_sum"], o["ring_cnt"]
+                    if state is not None:
+                        state.planes[_lib.PLANE_PD_CUR][s, y:y + h, x:x + w] = g
+                        if (p.ops & SQ_PD_SET_REF) and sel:
+                            state.planes[_lib.PLANE_PD_REF][s, y:y + h, x:x + w] = g
+                            state.planes[_lib.PLANE_FLAGS][s, y:y + h, x:x + w] |= 1
+                if (p.ops & (SQ_CD_CALIBRATE | SQ_CD_DETECT | SQ_CD_UPDATE)) and sel and state is not None:
+                    g = O.square_preprocess(sq, p.cd_blur)
+                    M = state.planes[_lib.PLANE_CD_MEAN][s, y:y + h, x:x + w]
+                    V = state.planes[_lib.PLANE_CD_VAR][s, y:y + h, x:x + w]
+                    has_cd = bool(fl & 2)
+                    if p.ops & SQ_CD_CALIBRATE:
+                        m, v = O.cd_calibrate(g, p.initial_variance)
+                        M[...] = m; V[...] = v
+                        state.planes[_lib.PLANE_FLAGS][s, y:y + h, x:x + w] |= 2
+                        has_cd = True
+                    if has_cd:
+                        m, v = np.array(M, np.float32), np.array(V, np.float32)
+                        if p.ops & SQ_CD_DETECT:
+                            cnt, zmax = O.cd_detect(g, m, v, p.z_threshold)
+                            st["cd_changed"], st["cd_zmax"], st["cd_valid"] = cnt, zmax, 1
+                        if p.ops & SQ_CD_UPDATE:
+                            # the exact f32 (alpha, 1-alpha) pair the kernel receives
+                            m2, v2 = np.array(M, np.float32), np.array(V, np.float32)
+                            O.lib().orc_cd_update(g.ctypes.data_as(O.oracle.C.c_void_p), O.oracle.C.c_long(g.size),
+                                                  O.oracle.C.c_float(p.alpha), O.oracle.C.c_float(p.one_minus_alpha),
+                                                  m2.ctypes.data_as(O.oracle.C.c_void_p), v2.ctypes.data_as(O.oracle.C.c_void_p))
+                            M[...] = m2; V[...] = v2
+        return out if want_stats else None

@@ -1,0 +1,110 @@
+"""CPU: libcvb200.so loads, exports every symbol include/cvb200.h declares, its host-side helpers
+(tables, kernels, perspective solve) agree with the oracle, and it refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from chessboard_vision_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cvb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _lib.load()
+    names = header_symbols()
+    assert len(names) >= 45
+    bound = {n for n, _, _ in _lib.SYMBOLS}
+    for n in names:
+        assert hasattr(lib, n), "libcvb200.so does not export %s" % n
+        assert n in bound, "%s is declared in the header but not bound in _lib.SYMBOLS" % n
+    assert bound <= set(names), "binding lists symbols the header does not declare: %s" % (bound - set(names))
+    assert lib.cvb_version() == 100
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(_lib.SquareStats) == 128
+    assert C.sizeof(_lib.Rect) == 16
+    assert C.sizeof(_lib.EnhanceParams) == 40
+    assert C.sizeof(_lib.SquareParams) == 32
+
+
+def test_tables_equal_oracle(oracle):
+    lib = _lib.load()
+    g = np.empty(256, np.uint16); c = np.empty(2048, np.uint16); y = np.empty(512, np.int32)
+    ig = np.empty(4096, np.uint8); lt = np.empty(2048, np.uint8)
+    assert lib.cvb_get_tables(g.ctypes.data, c.ctypes.data, y.ctypes.data, ig.ctypes.data, lt.ctypes.data) == 0
+    t = oracle.tables()
+    assert np.array_equal(g, t["gamma"]) and np.array_equal(c, t["cbrt"][:2048])
+    assert np.array_equal(y, t["lab2yf"]) and np.array_equal(ig, t["invgamma"])
+    L = np.clip((296 * t["cbrt"][:2048].astype(np.int64) - 1336934 + 16384) >> 15, 0, 255)
+    assert np.array_equal(lt, L.astype(np.uint8))
+    color = np.empty(768, np.float32); space = np.empty(81, np.float32)
+    for sc, ss in ((75.0, 75.0), (30.0, 10.0)):
+        assert lib.cvb_get_bilateral_tables(sc, ss, color.ctypes.data, space.ctypes.data) == 0
+        oc, osp, dy, dx = oracle.bilateral_tables(9, sc, ss)
+        assert np.array_equal(color, oc)
+        assert len(osp) == 49 and np.count_nonzero(space) == 49
+        for w, yy, xx in zip(osp, dy, dx):
+            assert space[(yy + 4) * 9 + xx + 4] == w
+
+
+@pytest.mark.parametrize("k", list(range(1, 32, 2)))
+def test_gaussian_kernels_equal_oracle(oracle, k):
+    q = np.zeros(31, np.int32)
+    assert _lib.load().cvb_gaussian_kernel_q8(k, q.ctypes.data) == 0
+    assert np.array_equal(q[:k], oracle.gaussian_kernel_q8(k)) and q[:k].sum() == 256
+
+
+def test_bad_gaussian_kernel_is_an_error():
+    q = np.zeros(31, np.int32)
+    lib = _lib.load()
+    for k in (0, 2, 33, -1):
+        assert lib.cvb_gaussian_kernel_q8(k, q.ctypes.data) == -1
+        assert b"ksize" in lib.cvb_last_error()
+
+
+def test_perspective_transform_equals_oracle(oracle):
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    dst = np.float32([[0, 0], [620, 0], [0, 620], [620, 620]])
+    for _ in range(200):
+        pts = np.float32([[0, 0], [1920, 0], [0, 1080], [1920, 1080]]) + rng.uniform(-300, 300, (4, 2)).astype(np.float32)
+        M = np.empty(9)
+        assert lib.cvb_get_perspective_transform(pts.ctypes.data, dst.ctypes.data, M.ctypes.data) == 0
+        assert np.array_equal(M.reshape(3, 3), oracle.get_perspective(pts, dst))
+    deg = np.float32([[0, 0], [1, 1], [2, 2], [3, 3]])
+    assert lib.cvb_get_perspective_transform(deg.ctypes.data, dst.ctypes.data, M.ctypes.data) == -1
+
+
+def test_no_gpu_means_no_handle():
+    """There is no CPU fallback: on a box without a CUDA device cvb_create fails loudly."""
+    lib = _lib.load()
+    if lib.cvb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.cvb_create(0, C.byref(h))
+    assert rc == -3 and not h.value
+    assert b"no CPU fallback" in lib.cvb_last_error()
+    from chessboard_vision_b200.engine import Engine
+    with pytest.raises(_lib.CvbError):
+        Engine(0)
+
+
+def test_product_does_not_import_the_oracle():
+    """The shipped package must never route through oracle/ (tier rule)."""
+    pkg = os.path.join(ROOT, "chessboard_vision_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "cvb_oracle" not in txt, f
