@@ -15,6 +15,7 @@
 // Compiled with -fmad=false: every fused multiply-add below is explicit.
 #include "cvb_device.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 
 int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g)
@@ -98,7 +99,15 @@ int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr)
 //   grid = (tiles, row-splits, frames); warp-private 256-bin histograms in smem.
 //   Tiles are laid over the REFLECT_101-extended image (clahe.cpp), so right /
 //   bottom tiles of non-divisible sizes read mirrored pixels.
+//   Fast path (tile inside the image, 16-pixel groups 16-byte aligned): each thread
+//   pulls 16 pixels as three 128-bit loads; L comes from two shared LUTs
+//   (per-channel Y contributions, then Y-index -> L).
 // ---------------------------------------------------------------------------------------
+CVB_DEV int l_of_bgr(const int (*tY)[256], const uint8_t *ltab, uint32_t b, uint32_t g, uint32_t r)
+{
+    return ltab[(tY[0][b] + tY[1][g] + tY[2][r] + 2048) >> 12];
+}
+
 template <bool FROM_BGR>
 __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ src, int H, int W, ClaheGeom g,
                                                    const CvbTables *__restrict__ tabs, int32_t *__restrict__ hist,
@@ -114,7 +123,8 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
     if (FROM_BGR) {
         const int gv = tabs->gamma[tid];
         s_tY[0][tid] = gv * 296; s_tY[1][tid] = gv * 2929; s_tY[2][tid] = gv * 871;
-        for (int i = tid; i < 2048; i += 256) s_ltab[i] = tabs->ltab[i];
+        for (int i = tid; i < 2048 / 4; i += 256)
+            reinterpret_cast<uint32_t *>(s_ltab)[i] = reinterpret_cast<const uint32_t *>(tabs->ltab)[i];
     }
     if (minmax_init && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         minmax_init[2 * frame] = 255; minmax_init[2 * frame + 1] = 0;
@@ -122,20 +132,54 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
     __syncthreads();
     const int rows_per = (g.tile_h + gridDim.y - 1) / gridDim.y;
     const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, g.tile_h);
-    const uint8_t *img = src + (size_t)frame * H * W * (FROM_BGR ? 3 : 1);
-    const int npx = (r1 - r0) * g.tile_w;
+    constexpr int CH = FROM_BGR ? 3 : 1;
+    const uint8_t *img = src + (size_t)frame * H * W * CH;
     int *my = s_hist[warp];
-    for (int i = tid; i < npx; i += 256) {
-        const int ry = i / g.tile_w, rx = i - ry * g.tile_w;
-        const int sy = reflect101(ty * g.tile_h + r0 + ry, H), sx = reflect101(tx * g.tile_w + rx, W);
-        int L;
-        if (FROM_BGR) {
-            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
-            L = s_ltab[(s_tY[0][p[0]] + s_tY[1][p[1]] + s_tY[2][p[2]] + 2048) >> 12];
-        } else {
-            L = img[(size_t)sy * W + sx];
+    const int x_lo = tx * g.tile_w, y_lo = ty * g.tile_h + r0;
+    const bool inside = x_lo + g.tile_w <= W && ty * g.tile_h + r1 <= H;
+    const bool fast = inside && (g.tile_w % 16 == 0) && (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (fast) {
+        const int gpr = g.tile_w >> 4;                       // 16-pixel groups per tile row
+        const int ngroups = (r1 - r0) * gpr;
+        for (int i = tid; i < ngroups; i += 256) {
+            const int ry = i / gpr, gx = i - ry * gpr;
+            const size_t px = (size_t)(y_lo + ry) * W + x_lo + (gx << 4);
+            if (FROM_BGR) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(img + px * 3);
+                const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {       // 4 pixels per 3 words: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                    const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff)], 1);
+                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff)], 1);
+                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff)], 1);
+                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24)], 1);
+                }
+            } else {
+                const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img + px));
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    atomicAdd(&my[w[k] & 0xff], 1); atomicAdd(&my[(w[k] >> 8) & 0xff], 1);
+                    atomicAdd(&my[(w[k] >> 16) & 0xff], 1); atomicAdd(&my[w[k] >> 24], 1);
+                }
+            }
         }
-        atomicAdd(&my[L], 1);
+    } else {
+        const int npx = (r1 - r0) * g.tile_w;
+        for (int i = tid; i < npx; i += 256) {
+            const int ry = i / g.tile_w, rx = i - ry * g.tile_w;
+            const int sy = reflect101(y_lo + ry, H), sx = reflect101(x_lo + rx, W);
+            int L;
+            if (FROM_BGR) {
+                const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
+                L = l_of_bgr(s_tY, s_ltab, p[0], p[1], p[2]);
+            } else {
+                L = img[(size_t)sy * W + sx];
+            }
+            atomicAdd(&my[L], 1);
+        }
     }
     __syncthreads();
     int tot = 0;
@@ -252,7 +296,8 @@ struct FusedArgs {
     const CvbTables *tabs;
     const uint8_t *lut;       // CLAHE LUTs of all frames (LIGHT)
     ClaheGeom g;
-    const float *wlut;        // [10][768] space*colour weights (device)
+    const float *wlut;        // [10][768] space*colour weights, or [768] colour weights when !FOLD (device)
+    float sw[81];             // spatial weights [dy+4][dx+4] (used when !FOLD)
     int32_t *minmax;          // per frame {min,max} or null
 };
 
@@ -270,7 +315,7 @@ struct AxisInfo {         // one per staged column / row
     float a, a1;          // blend factors
 };
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, bool FOLD = true>
 struct FusedCfg {
     static constexpr int BX = SHARP ? 2 : 0, BY = SHARP ? 1 : 0;   // B halo around the tile
     static constexpr int BW = TW + 2 * BX, BH = TH + 2 * BY;
@@ -281,7 +326,8 @@ struct FusedCfg {
     static constexpr size_t offA = 0;
     static constexpr size_t offB = offA + (size_t)AW * AH * 4;
     static constexpr size_t offW = offB + (BIL ? (size_t)BW * BH * 4 : 0);
-    static constexpr size_t offT = offW + (BIL ? 10 * 768 * 4 : 0);
+    static constexpr int NLUT = FOLD ? 10 : 1;
+    static constexpr size_t offT = offW + (BIL ? NLUT * 768 * 4 : 0);
     static constexpr size_t offX = offT + (LIGHT ? sizeof(SmemColorTables) : 0);
     static constexpr size_t smem_bytes = offX + (size_t)(AW + AH) * sizeof(AxisInfo) + (size_t)(2 * TW + 2 * TH) * 2;
 };
@@ -292,10 +338,10 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
     return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540u | (unsigned)k)) - 8388608.0f;
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
-__global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, bool FOLD = true>
+__global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
-    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP>;
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, FOLD>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw + Cfg::offA);
@@ -315,9 +361,9 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     if (BIL) {
         const uint4 *gw = reinterpret_cast<const uint4 *>(a.wlut);
         uint4 *dw = reinterpret_cast<uint4 *>(smem_raw + Cfg::offW);
-        for (int i = tid; i < 10 * 768 / 4; i += 256) dw[i] = __ldg(gw + i);
+        for (int i = tid; i < Cfg::NLUT * 768 / 4; i += NT) dw[i] = __ldg(gw + (FOLD ? 0 : 0) + i);
     }
-    for (int i = tid; i < AW + AH; i += 256) {
+    for (int i = tid; i < AW + AH; i += NT) {
         AxisInfo ai;
         const bool col = i < AW;
         const int p = col ? reflect101(ax0 + i, W) : reflect101(ay0 + (i - AW), H);
@@ -330,12 +376,12 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
         sAx[i] = ai;
     }
     if (SHARP) {
-        for (int i = tid; i < TW; i += 256) {
+        for (int i = tid; i < TW; i += NT) {
             const int X = min(x0 + i, W - 1);
             sNb[i] = (int16_t)(reflect101(X - 1, W) - bx0);
             sNb[TW + i] = (int16_t)(reflect101(X + 1, W) - bx0);
         }
-        for (int i = tid; i < TH; i += 256) {
+        for (int i = tid; i < TH; i += NT) {
             const int Y = min(y0 + i, H - 1);
             sNb[2 * TW + i] = (int16_t)(reflect101(Y - 1, H) - by0);
             sNb[2 * TW + TH + i] = (int16_t)(reflect101(Y + 1, H) - by0);
@@ -346,7 +392,7 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     // ---- A ----
     {
         const uint8_t *lut = LIGHT ? a.lut + (size_t)frame * a.g.tiles_x * a.g.tiles_y * 256 : nullptr;
-        for (int i = tid; i < AW * AH; i += 256) {
+        for (int i = tid; i < AW * AH; i += NT) {
             const int ly = i / AW, lx = i - ly * AW;
             const AxisInfo cx = sAx[lx], cy = sAx[AW + ly];
             const uint8_t *p = img + ((size_t)cy.src * W + cx.src) * 3;
@@ -373,7 +419,7 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     // ---- B ----
     if (BIL) {
         constexpr int RUNS = Cfg::RUNS;
-        for (int item = tid; item < BH * RUNS; item += 256) {
+        for (int item = tid; item < BH * RUNS; item += NT) {
             const int row = item / RUNS, r4 = (item - row * RUNS) * 4;
             const int Y = by0 + row, X = bx0 + r4;
             if (Y < 0 || Y >= H || X + 3 < 0 || X >= W) continue;
@@ -412,7 +458,8 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
                     for (int dx = -4; dx <= 4; ++dx) {
                         if (dy * dy + dx * dx > 16) continue;
                         const int c = j + 4 + dx;
-                        const float w = sW[r2_class(dy * dy + dx * dx) * 768 + __vsadu4(px[c], ctr[j])];
+                        const float w = FOLD ? sW[r2_class(dy * dy + dx * dx) * 768 + __vsadu4(px[c], ctr[j])]
+                                             : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[__vsadu4(px[c], ctr[j])]);
                         wsum[j] = __fadd_rn(wsum[j], w);
                         sb[j] = __fmaf_rn(fb[c], w, sb[j]);
                         sg[j] = __fmaf_rn(fg[c], w, sg[j]);
@@ -436,10 +483,10 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     // ---- C ----  (results of the tile go to sOut = the start of sA, free once B is done)
     uint32_t *sOut = sA;
     int vmin = 255, vmax = 0;
-    uint32_t keep[(TW * TH + 255) / 256];
+    uint32_t keep[(TW * TH + NT - 1) / NT];
 #pragma unroll
-    for (int it = 0; it < (TW * TH + 255) / 256; ++it) {
-        const int i = tid + it * 256;
+    for (int it = 0; it < (TW * TH + NT - 1) / NT; ++it) {
+        const int i = tid + it * NT;
         uint32_t q = 0;
         if (i < TW * TH) {
             const int ty = i / TW, tx = i - ty * TW;
@@ -476,15 +523,15 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     }
     __syncthreads();                      // every read of sB (may alias sA) is done
 #pragma unroll
-    for (int it = 0; it < (TW * TH + 255) / 256; ++it) {
-        const int i = tid + it * 256;
+    for (int it = 0; it < (TW * TH + NT - 1) / NT; ++it) {
+        const int i = tid + it * NT;
         if (i < TW * TH) sOut[i] = keep[it];
     }
     __syncthreads();
     uint8_t *out = a.dst + (size_t)frame * H * W * 3;
     const bool fast = (W % 4 == 0) && (x0 + TW <= W) && ((reinterpret_cast<uintptr_t>(a.dst) & 3) == 0);
     constexpr int GROUPS = TW / 4;
-    for (int item = tid; item < TH * GROUPS; item += 256) {
+    for (int item = tid; item < TH * GROUPS; item += NT) {
         const int ty = item / GROUPS, tx4 = (item - ty * GROUPS) * 4;
         const int Y = y0 + ty;
         if (Y >= H) break;
@@ -514,11 +561,11 @@ __global__ void __launch_bounds__(256) k_fused(const FusedArgs a)
     }
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, bool FOLD = true>
 static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
-    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP>;
-    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP>;
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, FOLD>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, FOLD>;
     static bool attr_done = false;
     if (!attr_done) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
@@ -526,7 +573,7 @@ static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
     }
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, n);
     PROF(h, "k_fused");
-    kern<<<grid, 256, Cfg::smem_bytes, h->stream>>>(a);
+    kern<<<grid, NT, Cfg::smem_bytes, h->stream>>>(a);
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
@@ -541,7 +588,7 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
     if (bilateral) {
         if (h->color_sigma != sigma_color || h->space_sigma != sigma_space || !h->d_color) {
-            std::vector<float> color(768), space(81), wl(10 * 768);
+            std::vector<float> color(768), space(81), wl(11 * 768);
             cvb_host_bilateral_tables(sigma_color, sigma_space, color.data(), space.data());
             for (int c = 0; c < 10; ++c) {
                 // any tap of that radius (weights depend on dy^2+dx^2 only)
@@ -554,6 +601,7 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
                     wl[c * 768 + i] = prod;
                 }
             }
+            for (int i = 0; i < 768; ++i) wl[10 * 768 + i] = color[i];
             if (!h->d_color) CVB_CHECK_CUDA(cudaMalloc(&h->d_color, wl.size() * sizeof(float)));
             CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
             CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // pageable source dies at scope end
@@ -561,13 +609,16 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
         }
         a.wlut = h->d_color;
     }
-    constexpr int TW = 60, TH = 30;
-    if (light && bilateral && sharpen) return launch_fused_t<TW, TH, true, true, true>(h, a, n);
-    if (!light && bilateral && !sharpen) return launch_fused_t<TW, TH, false, true, false>(h, a, n);
-    if (!light && !bilateral && sharpen) return launch_fused_t<TW, TH, false, false, true>(h, a, n);
-    if (!light && bilateral && sharpen) return launch_fused_t<TW, TH, false, true, true>(h, a, n);
-    if (light && !bilateral && !sharpen) return launch_fused_t<TW, TH, true, false, false>(h, a, n);
-    if (light && bilateral && !sharpen) return launch_fused_t<TW, TH, true, true, false>(h, a, n);
+    memset(a.sw, 0, sizeof a.sw);
+    if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
+    // Tile shapes measured on B200 at 1080p (profiles/r01_notes.md): 120x60 outputs per 512-thread CTA tile 1080p and
+    // 4K exactly and keep the halo overheads low (B 1.10x, A 1.28x); the folded 30 KB weight table beat the 3 KB one.
+    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, true>(h, a, n);
+    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, true>(h, a, n);
+    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, true>(h, a, n);
+    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, true>(h, a, n);
+    if (!light && !bilateral && sharpen) return launch_fused_t<60, 30, false, false, true>(h, a, n);
+    if (light && !bilateral && !sharpen) return launch_fused_t<60, 30, true, false, false>(h, a, n);
     cvb_set_error("unsupported fused stage combination");
     return CVB_ERR_INVALID;
 }
@@ -722,12 +773,11 @@ int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int 
 
 // ---------------------------------------------------------------------------------------
 // Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 128x32, halo 2.
-//   1  rows of the sharpened frame (tile + 4 columns each side, clipped to the image)
-//      are staged in shared memory with 16-byte transfers;
-//   2  groups of 4 pixels: min-max map (skipped when it is the identity), write the
-//      enhanced pixels (3 words), gray (1 word) and keep gray in shared memory;
-//   3  horizontal [1 4 6 4 1]; 4  vertical [1 4 6 4 1], (sum+128)>>8, histogram.
-// Mirror columns / rows (REFLECT_101 of GaussianBlur) are taken from the staged rows.
+//   1  groups of 4 pixels (three 32-bit words) straight from the sharpened frame:
+//      min-max map (skipped when it is the identity), write the enhanced pixels (3 words)
+//      and gray (1 word), keep gray (+ halo) in shared memory;
+//   2  horizontal [1 4 6 4 1];  3  vertical [1 4 6 4 1], (sum+128)>>8, histogram.
+// Mirror rows / columns (REFLECT_101 of GaussianBlur) are resolved when gray is staged.
 // ---------------------------------------------------------------------------------------
 template <bool NORM>
 __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src, int H, int W,
@@ -737,14 +787,13 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
 {
     constexpr int FW = 128, FH = 32, R = 2, PADX = 4;
     constexpr int GH = FH + 2 * R;                 // staged rows
-    constexpr int SW = FW + 2 * PADX;              // staged / gray columns: X = x0-4 .. x0+131
-    constexpr int ROWP = (SW * 3 + 15 + 15) / 16 * 16;
-    constexpr int VPR = ROWP / 16;                 // vector slots per staged row
-    __shared__ __align__(16) uint8_t s_raw[GH][ROWP];
+    constexpr int SW = FW + 2 * PADX;              // gray columns: X = x0-4 .. x0+131
+    constexpr int NG = SW / 4;                     // 34 groups per row
     __shared__ __align__(16) uint8_t s_g[GH][SW];
     __shared__ __align__(8) uint16_t s_h[GH][FW];
     __shared__ int s_hist[8][256];
     __shared__ uint8_t s_map[256];
+    __shared__ int s_rowofs[GH];                   // mirrored source row of each staged row
     const int tid = threadIdx.x, frame = blockIdx.z;
     const int x0 = blockIdx.x * FW, y0 = blockIdx.y * FH;
     const size_t fo = (size_t)frame * H * W;
@@ -757,42 +806,23 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
         identity = (lo == 0 && hi == 255);
         if (!identity) s_map[tid] = (uint8_t)normalize_value(tid, lo, hi);
     }
-    const int cx0 = max(x0 - PADX, 0), cx1 = min(x0 + FW + PADX, W);
-    const int span = (cx1 - cx0) * 3;
-    // ---- 1: stage rows; one (row, 16-byte slot) item per thread step ----
-    for (int item = tid; item < GH * VPR; item += 256) {
-        const int ly = item / VPR, v = item - ly * VPR;
-        const uint8_t *g = img + ((size_t)reflect101(y0 - R + ly, H) * W + cx0) * 3;
-        uint8_t *s = s_raw[ly];
-        const int phase = span_phase(g);
-        const int head = min(span, (16 - phase) & 15);
-        const int body = (span - head) >> 4;
-        if (v < body) {
-            reinterpret_cast<uint4 *>(s + phase + head)[v] = __ldg(reinterpret_cast<const uint4 *>(g + head) + v);
-        } else if (v == VPR - 1) {
-            for (int i = 0; i < head; ++i) s[phase + i] = __ldg(g + i);
-        } else if (v == VPR - 2) {
-            for (int i = head + (body << 4); i < span; ++i) s[phase + i] = __ldg(g + i);
-        }
-    }
+    if (tid < GH) s_rowofs[tid] = reflect101(y0 - R + tid, H);
     __syncthreads();
-    // ---- 2: map, emit enhanced + gray, keep gray ----
-    constexpr int NG = SW / 4;                      // 34 groups per row, group gi covers X = x0-4+4gi ..
-    const bool al4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    // ---- 1 ----
+    const bool al4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+    const bool out4 = al4 && ((reinterpret_cast<uintptr_t>(enhanced) & 3) == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0);
     for (int item = tid; item < GH * NG; item += 256) {
         const int ly = item / NG, gi = item - ly * NG;
-        const int Y = y0 - R + ly;
-        const int sy = reflect101(Y, H);
         const int X = x0 - PADX + 4 * gi;
-        const uint8_t *rowg = img + ((size_t)sy * W + cx0) * 3;
-        const uint8_t *s = s_raw[ly] + span_phase(rowg);
+        const int sy = s_rowofs[ly];
+        const uint8_t *rowp = img + (size_t)sy * W * 3;
         uint32_t gpack = 0;
         if (X >= 0 && X + 3 < W) {
-            const uint8_t *p = s + (X - cx0) * 3;
+            const uint8_t *p = rowp + (size_t)X * 3;
             uint32_t w0, w1, w2;
-            if (al4) {   // (row start + X*3) is a multiple of 4 when W%4==0, X%4==0 and the frame base is aligned
+            if (al4) {
                 const uint32_t *p32 = reinterpret_cast<const uint32_t *>(p);
-                w0 = p32[0]; w1 = p32[1]; w2 = p32[2];
+                w0 = __ldg(p32); w1 = __ldg(p32 + 1); w2 = __ldg(p32 + 2);
             } else {
                 w0 = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
                 w1 = p[4] | (p[5] << 8) | (p[6] << 16) | ((uint32_t)p[7] << 24);
@@ -809,11 +839,12 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
             const int g2 = gray_px((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
             const int g3 = gray_px((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
             gpack = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
+            const int Y = y0 - R + ly;
             if (ly >= R && ly < GH - R && Y < H && gi >= 1 && gi <= FW / 4) {   // interior of this tile
                 const size_t po = (size_t)Y * W + X;
                 if (enhanced) {
                     uint8_t *o = enhanced + (fo + po) * 3;
-                    if (al4 && (reinterpret_cast<uintptr_t>(enhanced) & 3) == 0) {
+                    if (out4) {
                         uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
                         o32[0] = w0; o32[1] = w1; o32[2] = w2;
                     } else {
@@ -823,19 +854,19 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                 }
                 if (gray) {
                     uint8_t *o = gray + fo + po;
-                    if (al4 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0) *reinterpret_cast<uint32_t *>(o) = gpack;
+                    if (out4) *reinterpret_cast<uint32_t *>(o) = gpack;
                     else
                         for (int i = 0; i < 4; ++i) o[i] = (uint8_t)(gpack >> (8 * i));
                 }
             }
         } else {
-            // group touching an image edge: per pixel, mirror columns come from the staged span
+            // group touching an image edge: per pixel, with mirrored columns
+            const int Y = y0 - R + ly;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int Xj = X + j;
                 if (Xj < x0 - R || Xj >= x0 + FW + R || Xj >= W + R) continue;   // never read by a valid output
-                const int sx = reflect101(Xj, W);
-                const uint8_t *p = s + (sx - cx0) * 3;
+                const uint8_t *p = rowp + (size_t)reflect101(Xj, W) * 3;
                 int b = p[0], g = p[1], r = p[2];
                 if (NORM && !identity) { b = s_map[b]; g = s_map[g]; r = s_map[r]; }
                 const int gv = gray_px(b, g, r);
@@ -853,7 +884,7 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
         *reinterpret_cast<uint32_t *>(&s_g[ly][4 * gi]) = gpack;
     }
     __syncthreads();
-    // ---- 3: horizontal pass, 4 outputs per item (output x <-> gray columns x+2 .. x+6) ----
+    // ---- 2: horizontal pass, 4 outputs per item (output x <-> gray columns x+2 .. x+6) ----
     for (int item = tid; item < GH * (FW / 4); item += 256) {
         const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
         const uint32_t *gp = reinterpret_cast<const uint32_t *>(&s_g[ly][x]);
@@ -865,32 +896,33 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
         *reinterpret_cast<uint2 *>(&s_h[ly][x]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
     __syncthreads();
-    // ---- 4: vertical pass + histogram ----
+    // ---- 3: vertical pass + histogram ----
     int *myh = s_hist[tid >> 5];
+    const bool b4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(blurred) & 3) == 0);
     for (int item = tid; item < FH * (FW / 4); item += 256) {
         const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
         const int Y = y0 + ly, X = x0 + x;
         if (Y >= H || X >= W) continue;
-        uint32_t lo = 0, hi = 0;      // 16-bit lanes: outputs (0,1) and (2,3); sums <= 255*256 fit
-        {
-            const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
-            const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
-            const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
-            const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
-            const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
-            // per-lane sums stay below 2^16 (max 255*256 = 65280) so no carry crosses lanes
-            lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
-            hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
-        }
+        const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
+        const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
+        const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
+        const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
+        const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
+        // two 16-bit lanes per word; each lane's sum is <= 255*256 = 65280, so no carry crosses lanes
+        const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
+        const uint32_t hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
         const int o0 = ((lo & 0xffff) + 128) >> 8, o1 = ((lo >> 16) + 128) >> 8;
         const int o2 = ((hi & 0xffff) + 128) >> 8, o3 = ((hi >> 16) + 128) >> 8;
         const int ov[4] = {o0, o1, o2, o3};
         const int nvalid = min(4, W - X);
-        if (hist)
-            for (int j = 0; j < nvalid; ++j) atomicAdd(&myh[ov[j]], 1);
+        if (hist) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < nvalid) atomicAdd(&myh[ov[j]], 1);
+        }
         if (blurred) {
             uint8_t *o = blurred + fo + (size_t)Y * W + X;
-            if (nvalid == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0)
+            if (nvalid == 4 && b4)
                 *reinterpret_cast<uint32_t *>(o) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
             else
                 for (int j = 0; j < nvalid; ++j) o[j] = (uint8_t)ov[j];

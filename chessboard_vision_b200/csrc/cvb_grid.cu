@@ -90,22 +90,58 @@ struct SquareArgs {
     cvb_square_stats *stats;
 };
 
-CVB_DEV int blur_at(const uint16_t *s_h, const int *q, int k, int x, int y, int w, int h)
+// single-bounce REFLECT_101, valid while the overshoot is smaller than n
+CVB_DEV int reflect_near(int p, int n)
 {
-    const int r = k >> 1;
-    uint32_t s = 0;
-    for (int i = 0; i < k; ++i) s += (uint32_t)q[i] * s_h[reflect101(y + i - r, h) * w + x];
-    return (int)((s + 32768u) >> 16);
+    p = p < 0 ? -p : p;
+    return p >= n ? 2 * n - 2 - p : p;
 }
-CVB_DEV void hpass(const uint8_t *s_g, uint16_t *s_h, const int *q, int k, int w, int h, int tid)
+
+// horizontal Q8 pass over the whole square (rows by warp, columns by lane: no divisions)
+template <int K>
+CVB_DEV void hpass(const uint8_t *s_g, uint16_t *s_h, const int *q, int k_rt, int w, int h, bool near_ok)
 {
-    const int r = k >> 1;
-    for (int i = tid; i < w * h; i += 256) {
-        const int y = i / w, x = i - y * w;
-        uint32_t s = 0;
-        for (int j = 0; j < k; ++j) s += (uint32_t)q[j] * s_g[y * w + reflect101(x + j - r, w)];
-        s_h[i] = (uint16_t)s;
+    const int k = K ? K : k_rt, r = k >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int y = warp; y < h; y += 8) {
+        const uint8_t *row = s_g + y * w;
+        for (int x = lane; x < w; x += 32) {
+            uint32_t s = 0;
+            if (K == 5) {
+                if (x >= 2 && x + 2 < w) {
+                    s = q[0] * row[x - 2] + q[1] * row[x - 1] + q[2] * row[x] + q[3] * row[x + 1] + q[4] * row[x + 2];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+                        s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - 2, w) : reflect101(x + j - 2, w)];
+                }
+            } else {
+                for (int j = 0; j < k; ++j)
+                    s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - r, w) : reflect101(x + j - r, w)];
+            }
+            s_h[y * w + x] = (uint16_t)s;
+        }
     }
+}
+template <int K>
+CVB_DEV int blur_at(const uint16_t *s_h, const int *q, int k_rt, int x, int y, int w, int h, bool near_ok)
+{
+    const int k = K ? K : k_rt, r = k >> 1;
+    uint32_t s = 0;
+    if (K == 5) {
+        if (y >= 2 && y + 2 < h) {
+            const uint16_t *c = s_h + (y - 2) * w + x;
+            s = q[0] * c[0] + q[1] * c[w] + q[2] * c[2 * w] + q[3] * c[3 * w] + q[4] * c[4 * w];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+                s += (uint32_t)q[i] * s_h[(near_ok ? reflect_near(y + i - 2, h) : reflect101(y + i - 2, h)) * w + x];
+        }
+    } else {
+        for (int i = 0; i < k; ++i)
+            s += (uint32_t)q[i] * s_h[(near_ok ? reflect_near(y + i - r, h) : reflect101(y + i - r, h)) * w + x];
+    }
+    return (int)((s + 32768u) >> 16);
 }
 
 __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
@@ -114,7 +150,7 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
     __shared__ unsigned long long s_acc[16];
     __shared__ unsigned s_cd_nan;
     __shared__ int s_cd_zbits;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sq = blockIdx.x, frame = blockIdx.y;
     const cvb_rect rc = a.rects[sq];
     const int w = rc.w, h = rc.h, n = w * h;
@@ -128,10 +164,12 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
 
     if (tid < 16) s_acc[tid] = 0ull;
     if (tid == 0) { s_cd_nan = 0; s_cd_zbits = __float_as_int(-INFINITY); }
-    for (int i = tid; i < n; i += 256) {
-        const int y = i / w, x = i - y * w;
-        const uint8_t *p = board + ((size_t)(rc.y + y) * a.BW + rc.x + x) * a.C;
-        s_g[i] = a.C == 3 ? (uint8_t)gray_px(p[0], p[1], p[2]) : p[0];
+    for (int y = warp; y < h; y += 8) {
+        const uint8_t *rowp = board + ((size_t)(rc.y + y) * a.BW + rc.x) * a.C;
+        if (a.C == 3)
+            for (int x = lane; x < w; x += 32) s_g[y * w + x] = (uint8_t)gray_px(rowp[3 * x], rowp[3 * x + 1], rowp[3 * x + 2]);
+        else
+            for (int x = lane; x < w; x += 32) s_g[y * w + x] = rowp[x];
     }
     __syncthreads();
 
@@ -139,13 +177,18 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
     const bool state = a.flags != nullptr;
     const int fl0 = state ? a.flags[first] : 0;
     const bool has_ref = (fl0 & 1) != 0;
-    bool has_cd = (fl0 & 2) != 0;
+    const bool has_cd = (fl0 & 2) != 0;
 
-    // ---- PieceDetector pass (blur pd_blur) ----
     const bool need_pd = (ops & (CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF)) != 0;
     const bool need_cd = (ops & (CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE)) != 0 && selected && state;
     const bool same_blur = a.p.pd_blur == a.p.cd_blur;
-    if (need_pd || (need_cd && same_blur)) hpass(s_g, s_h, a.pd_q, a.p.pd_blur, w, h, tid);
+    const bool pass1 = need_pd || (need_cd && same_blur);
+    const bool near_pd = w > (a.p.pd_blur >> 1) && h > (a.p.pd_blur >> 1);
+    const bool near_cd = w > (a.p.cd_blur >> 1) && h > (a.p.cd_blur >> 1);
+    if (pass1) {
+        if (a.p.pd_blur == 5) hpass<5>(s_g, s_h, a.pd_q, 5, w, h, near_pd);
+        else hpass<0>(s_g, s_h, a.pd_q, a.p.pd_blur, w, h, near_pd);
+    }
     __syncthreads();
 
     unsigned sum = 0, sad = 0, csum = 0, ccnt = 0, bsum = 0, bcnt = 0;
@@ -182,35 +225,43 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
         }
     };
 
-    if (need_pd || (need_cd && same_blur)) {
-        for (int i = tid; i < n; i += 256) {
-            const int y = i / w, x = i - y * w;
-            const int gv = blur_at(s_h, a.pd_q, a.p.pd_blur, x, y, w, h);
-            const size_t o = so + (size_t)(rc.y + y) * a.BW + rc.x + x;
-            if (ops & CVB_SQ_PD_STATS) {
-                const int m = mask[i];
-                sum += gv; sumsq += (unsigned)(gv * gv);
-                if (has_ref) sad += (unsigned)abs(gv - (int)a.pd_ref[o]);
-                if (m & 1) { csum += gv; ++ccnt; }
-                if (m & 2) { bsum += gv; ++bcnt; }
+    if (pass1) {
+        const bool k5 = a.p.pd_blur == 5;
+        for (int y = warp; y < h; y += 8) {
+            const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
+            for (int x = lane; x < w; x += 32) {
+                const int gv = k5 ? blur_at<5>(s_h, a.pd_q, 5, x, y, w, h, near_pd)
+                                  : blur_at<0>(s_h, a.pd_q, a.p.pd_blur, x, y, w, h, near_pd);
+                const size_t o = orow + x;
+                if (ops & CVB_SQ_PD_STATS) {
+                    const int m = mask[y * w + x];
+                    sum += gv; sumsq += (unsigned)(gv * gv);
+                    if (has_ref) sad += (unsigned)abs(gv - (int)a.pd_ref[o]);
+                    if (m & 1) { csum += gv; ++ccnt; }
+                    if (m & 2) { bsum += gv; ++bcnt; }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (m & (4 << k)) { rsum[k] += gv; ++rcnt[k]; }
+                    for (int k = 0; k < 4; ++k)
+                        if (m & (4 << k)) { rsum[k] += gv; ++rcnt[k]; }
+                }
+                if (state && need_pd) a.pd_cur[o] = (uint8_t)gv;
+                if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { a.pd_ref[o] = (uint8_t)gv; a.flags[o] |= 1; }
+                if (need_cd && same_blur) cd_pixel(gv, o);
             }
-            if (state && need_pd) a.pd_cur[o] = (uint8_t)gv;
-            if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { a.pd_ref[o] = (uint8_t)gv; a.flags[o] |= 1; }
-            if (need_cd && same_blur) cd_pixel(gv, o);
         }
     }
     // ---- ChangeDetector pass when its blur differs ----
     if (need_cd && !same_blur) {
         __syncthreads();
-        hpass(s_g, s_h, a.cd_q, a.p.cd_blur, w, h, tid);
+        if (a.p.cd_blur == 5) hpass<5>(s_g, s_h, a.cd_q, 5, w, h, near_cd);
+        else hpass<0>(s_g, s_h, a.cd_q, a.p.cd_blur, w, h, near_cd);
         __syncthreads();
-        for (int i = tid; i < n; i += 256) {
-            const int y = i / w, x = i - y * w;
-            const int gv = blur_at(s_h, a.cd_q, a.p.cd_blur, x, y, w, h);
-            cd_pixel(gv, so + (size_t)(rc.y + y) * a.BW + rc.x + x);
+        for (int y = warp; y < h; y += 8) {
+            const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
+            for (int x = lane; x < w; x += 32) {
+                const int gv = a.p.cd_blur == 5 ? blur_at<5>(s_h, a.cd_q, 5, x, y, w, h, near_cd)
+                                                : blur_at<0>(s_h, a.cd_q, a.p.cd_blur, x, y, w, h, near_cd);
+                cd_pixel(gv, orow + x);
+            }
         }
     }
     if (!a.stats) return;

@@ -32,3 +32,9 @@ tot = sum(v[0] for v in prof.values())
 for k, (ms, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
     print("%-16s %8.3f ms/launch  %5.1f%%  (%.2f us/frame)" % (k, ms / c, 100 * ms / tot, ms / c / n * 1e3))
 print("total %.3f ms/step  -> %.0f frames/s" % (tot / steps, n * steps / tot * 1e3))
+if os.environ.get("CVB_CHECK"):
+    import oracle as O
+    for shp in ((270, 480), (133, 251)):
+        f = synth.board_frame(*shp, 3)
+        ok = np.array_equal(eng.process_pipeline(f), O.process_pipeline(f, True))
+        print("parity", shp, "OK" if ok else "MISMATCH")
