@@ -144,7 +144,8 @@ CVB_DEV int blur_at(const uint16_t *s_h, const int *q, int k_rt, int x, int y, i
     return (int)((s + 32768u) >> 16);
 }
 
-__global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
+template <int OPS>
+__global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
 {
     extern __shared__ __align__(16) uint8_t sq_smem[];
     __shared__ unsigned long long s_acc[16];
@@ -160,16 +161,29 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
     const size_t so = (size_t)(a.stream0 + frame) * plane;       // state slot offset
     const uint8_t *board = a.boards + (size_t)frame * plane * a.C;
     const bool selected = a.select ? a.select[sq] != 0 : true;
-    const int ops = a.p.ops;
+    const int ops = OPS >= 0 ? OPS : a.p.ops;     // compile-time mask strips the per-pixel flag tests
 
     if (tid < 16) s_acc[tid] = 0ull;
     if (tid == 0) { s_cd_nan = 0; s_cd_zbits = __float_as_int(-INFINITY); }
     for (int y = warp; y < h; y += 8) {
         const uint8_t *rowp = board + ((size_t)(rc.y + y) * a.BW + rc.x) * a.C;
-        if (a.C == 3)
-            for (int x = lane; x < w; x += 32) s_g[y * w + x] = (uint8_t)gray_px(rowp[3 * x], rowp[3 * x + 1], rowp[3 * x + 2]);
-        else
-            for (int x = lane; x < w; x += 32) s_g[y * w + x] = rowp[x];
+        if (a.C == 3) {
+            for (int xb = lane; xb < w; xb += 128) {
+                int c0[4], c1[4], c2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = xb + 32 * j;
+                    if (x < w) { c0[j] = __ldg(rowp + 3 * x); c1[j] = __ldg(rowp + 3 * x + 1); c2[j] = __ldg(rowp + 3 * x + 2); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = xb + 32 * j;
+                    if (x < w) s_g[y * w + x] = (uint8_t)gray_px(c0[j], c1[j], c2[j]);
+                }
+            }
+        } else {
+            for (int x = lane; x < w; x += 32) s_g[y * w + x] = __ldg(rowp + x);
+        }
     }
     __syncthreads();
 
@@ -191,6 +205,10 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
     }
     __syncthreads();
 
+    uint8_t *const pd_ref = a.pd_ref, *const pd_cur = a.pd_cur, *const flags = a.flags;
+    float *const cd_mean = a.cd_mean, *const cd_var = a.cd_var;
+    const float zthr = a.p.z_threshold, alpha = a.p.alpha, oma = a.p.one_minus_alpha, minvar = a.p.min_variance,
+                initvar = a.p.initial_variance;
     unsigned sum = 0, sad = 0, csum = 0, ccnt = 0, bsum = 0, bcnt = 0;
     unsigned rsum[4] = {0, 0, 0, 0}, rcnt[4] = {0, 0, 0, 0};
     unsigned long long sumsq = 0;
@@ -199,29 +217,38 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
     bool cd_nan = false;
     const uint8_t *mask = a.masks + a.mask_ofs[sq];
 
-    auto cd_pixel = [&](int gv, size_t o) {
-        const float gf = (float)gv;
-        float m, v;
-        if (ops & CVB_SQ_CD_CALIBRATE) {
-            m = gf; v = a.p.initial_variance;
-            a.cd_mean[o] = m; a.cd_var[o] = v;
-            a.flags[o] |= 2;
-        } else {
-            if (!has_cd) return;
-            m = a.cd_mean[o]; v = a.cd_var[o];
+    // Per row, a lane owns columns lane, lane+32, ... in batches of U: all state loads of a batch are issued
+    // before any arithmetic or store, so several memory round trips overlap (the loop is latency bound).
+    constexpr int U = 4;
+    auto cd_batch = [&](const int (&gv)[U], const bool (&ok)[U], size_t orow, int xb) {
+        float m[U], v[U];
+        const bool calib = (ops & CVB_SQ_CD_CALIBRATE) != 0;
+        if (!calib && !has_cd) return;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const size_t o = orow + xb + 32 * j;
+            if (calib) { m[j] = (float)gv[j]; v[j] = initvar; }
+            else if (ok[j]) { m[j] = cd_mean[o]; v[j] = cd_var[o]; }
         }
-        if (ops & CVB_SQ_CD_DETECT) {
-            const float z = __fdiv_rn(fabsf(__fsub_rn(gf, m)), __fsqrt_rn(v));
-            if (z > a.p.z_threshold) ++cd_cnt;
-            if (z != z) cd_nan = true; else cd_zmax = fmaxf(cd_zmax, z);
-        }
-        if (ops & CVB_SQ_CD_UPDATE) {
-            // change_detector.py:82-89, every product and sum rounded on its own
-            const float nm = __fadd_rn(__fmul_rn(a.p.one_minus_alpha, m), __fmul_rn(a.p.alpha, gf));
-            const float d = __fsub_rn(gf, nm);
-            float nv = __fadd_rn(__fmul_rn(a.p.one_minus_alpha, v), __fmul_rn(a.p.alpha, __fmul_rn(d, d)));
-            if (!(nv > a.p.min_variance) && nv == nv) nv = a.p.min_variance;   // np.maximum keeps NaN
-            a.cd_mean[o] = nm; a.cd_var[o] = nv;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (!ok[j]) continue;
+            const size_t o = orow + xb + 32 * j;
+            const float gf = (float)gv[j];
+            if (calib) { cd_mean[o] = m[j]; cd_var[o] = v[j]; flags[o] |= 2; }
+            if (ops & CVB_SQ_CD_DETECT) {
+                const float z = __fdiv_rn(fabsf(__fsub_rn(gf, m[j])), __fsqrt_rn(v[j]));
+                if (z > zthr) ++cd_cnt;
+                if (z != z) cd_nan = true; else cd_zmax = fmaxf(cd_zmax, z);
+            }
+            if (ops & CVB_SQ_CD_UPDATE) {
+                // change_detector.py:82-89, every product and sum rounded on its own
+                const float nm = __fadd_rn(__fmul_rn(oma, m[j]), __fmul_rn(alpha, gf));
+                const float d = __fsub_rn(gf, nm);
+                float nv = __fadd_rn(__fmul_rn(oma, v[j]), __fmul_rn(alpha, __fmul_rn(d, d)));
+                if (!(nv > minvar) && nv == nv) nv = minvar;   // np.maximum keeps NaN
+                cd_mean[o] = nm; cd_var[o] = nv;
+            }
         }
     };
 
@@ -229,23 +256,42 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
         const bool k5 = a.p.pd_blur == 5;
         for (int y = warp; y < h; y += 8) {
             const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
-            for (int x = lane; x < w; x += 32) {
-                const int gv = k5 ? blur_at<5>(s_h, a.pd_q, 5, x, y, w, h, near_pd)
-                                  : blur_at<0>(s_h, a.pd_q, a.p.pd_blur, x, y, w, h, near_pd);
-                const size_t o = orow + x;
-                if (ops & CVB_SQ_PD_STATS) {
-                    const int m = mask[y * w + x];
-                    sum += gv; sumsq += (unsigned)(gv * gv);
-                    if (has_ref) sad += (unsigned)abs(gv - (int)a.pd_ref[o]);
-                    if (m & 1) { csum += gv; ++ccnt; }
-                    if (m & 2) { bsum += gv; ++bcnt; }
+            for (int xb = lane; xb < w; xb += 32 * U) {
+                int gv[U], mk[U], rf[U];
+                bool ok[U];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (m & (4 << k)) { rsum[k] += gv; ++rcnt[k]; }
+                for (int j = 0; j < U; ++j) {
+                    const int x = xb + 32 * j;
+                    ok[j] = x < w;
+                    mk[j] = 0; rf[j] = 0; gv[j] = 0;
+                    if (ok[j]) {
+                        if (ops & CVB_SQ_PD_STATS) {
+                            mk[j] = mask[y * w + x];
+                            if (has_ref) rf[j] = pd_ref[orow + x];
+                        }
+                        gv[j] = k5 ? blur_at<5>(s_h, a.pd_q, 5, x, y, w, h, near_pd)
+                                   : blur_at<0>(s_h, a.pd_q, a.p.pd_blur, x, y, w, h, near_pd);
+                    }
                 }
-                if (state && need_pd) a.pd_cur[o] = (uint8_t)gv;
-                if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { a.pd_ref[o] = (uint8_t)gv; a.flags[o] |= 1; }
-                if (need_cd && same_blur) cd_pixel(gv, o);
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    if (!ok[j]) continue;
+                    const size_t o = orow + xb + 32 * j;
+                    const int g1 = gv[j];
+                    if (ops & CVB_SQ_PD_STATS) {
+                        const int m = mk[j];
+                        sum += g1; sumsq += (unsigned)(g1 * g1);
+                        if (has_ref) sad += (unsigned)abs(g1 - rf[j]);
+                        if (m & 1) { csum += g1; ++ccnt; }
+                        if (m & 2) { bsum += g1; ++bcnt; }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (m & (4 << k)) { rsum[k] += g1; ++rcnt[k]; }
+                    }
+                    if (state && need_pd) pd_cur[o] = (uint8_t)g1;
+                    if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { pd_ref[o] = (uint8_t)g1; flags[o] |= 1; }
+                }
+                if (need_cd && same_blur) cd_batch(gv, ok, orow, xb);
             }
         }
     }
@@ -257,10 +303,17 @@ __global__ void __launch_bounds__(256) k_squares(const SquareArgs a)
         __syncthreads();
         for (int y = warp; y < h; y += 8) {
             const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
-            for (int x = lane; x < w; x += 32) {
-                const int gv = a.p.cd_blur == 5 ? blur_at<5>(s_h, a.cd_q, 5, x, y, w, h, near_cd)
-                                                : blur_at<0>(s_h, a.cd_q, a.p.cd_blur, x, y, w, h, near_cd);
-                cd_pixel(gv, orow + x);
+            for (int xb = lane; xb < w; xb += 32 * U) {
+                int gv[U];
+                bool ok[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int x = xb + 32 * j;
+                    ok[j] = x < w;
+                    gv[j] = !ok[j] ? 0 : a.p.cd_blur == 5 ? blur_at<5>(s_h, a.cd_q, 5, x, y, w, h, near_cd)
+                                                           : blur_at<0>(s_h, a.cd_q, a.p.cd_blur, x, y, w, h, near_cd);
+                }
+                cd_batch(gv, ok, orow, xb);
             }
         }
     }
@@ -317,14 +370,30 @@ int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, 
         cvb_set_error("square of %d pixels needs %zu bytes of shared memory (max 204800)", max_px, smem);
         return CVB_ERR_INVALID;
     }
-    static size_t attr_set = 0;
-    if (smem > 48 * 1024 && smem > attr_set) {
-        CVB_CHECK_CUDA(cudaFuncSetAttribute(k_squares, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
     dim3 grid(n_sq, n);
+    // the common op masks get a specialised instance (flag tests folded at compile time)
+    void (*kern)(const SquareArgs) = k_squares<-1>;
+    switch (p.ops) {
+    case CVB_SQ_PD_STATS: kern = k_squares<CVB_SQ_PD_STATS>; break;
+    case CVB_SQ_PD_SET_REF: kern = k_squares<CVB_SQ_PD_SET_REF>; break;
+    case CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF: kern = k_squares<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF>; break;
+    case CVB_SQ_CD_CALIBRATE: kern = k_squares<CVB_SQ_CD_CALIBRATE>; break;
+    case CVB_SQ_CD_DETECT: kern = k_squares<CVB_SQ_CD_DETECT>; break;
+    case CVB_SQ_CD_UPDATE: kern = k_squares<CVB_SQ_CD_UPDATE>; break;
+    case CVB_SQ_PD_STATS | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE:
+        kern = k_squares<CVB_SQ_PD_STATS | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE>; break;
+    case CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE:
+        kern = k_squares<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE>; break;
+    default: break;
+    }
+    static std::map<void *, size_t> attr_set;
+    size_t &cur = attr_set[(void *)kern];
+    if (smem > 48 * 1024 && smem > cur) {
+        CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
     PROF(h, "k_squares");
-    k_squares<<<grid, 256, smem, h->stream>>>(a);
+    kern<<<grid, 256, smem, h->stream>>>(a);
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
