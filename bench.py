@@ -171,6 +171,16 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +209,7 @@ def main():
         pool.close()
         fps = per_step * args.steps / dt
         sample = "%d frames per step (of the %d-frame batch), %d processes x 1 OpenCV thread" % (per_step, args.frames, cores)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -210,7 +220,7 @@ def main():
                              "what": ("oracle/ref_cv2.py: the reference's own cv2/numpy call sequence on OpenCV %s" %
                                       __import__("cv2").__version__) if kind == "cv2" else
                                      "oracle/cvb_oracle.c scalar C restatement (cv2 not importable)"},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ this repo's arm
@@ -347,7 +357,7 @@ def main():
                        "api": "Engine.pipeline -> cvb_pipeline (pinned host frames in, per-square statistics + Otsu "
                               "thresholds out)"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.destroy_process_group()
 

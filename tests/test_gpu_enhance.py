@@ -188,3 +188,36 @@ def test_enhance_1080p_properties(engine, oracle):
     # idempotence of normalize on an already full-range image
     assert enh.min() == 0 and enh.max() == 255
     assert np.array_equal(engine.normalize(enh), enh)
+
+
+def test_enhance_4k_vs_oracle_and_stream_state(engine, oracle):
+    """BASELINE.json configs[4] shape: 3840x2160 frames, per-stream state resident on the GPU."""
+    from chessboard_vision_b200.engine import grid_rects, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE
+    H, W, S = 2160, 3840, 620
+    f0 = synth.board_frame(H, W, 40)
+    f1 = f0.copy(); f1[600:1500, 1400:2400] = 255
+    enh, g, b, T = engine.enhance(f0)
+    ref = oracle.process_pipeline(f0, use_fma=True)
+    assert np.array_equal(enh, ref)
+    rg, rb, rT, _ = oracle.prepare_analysis(ref, return_all=True)
+    assert T == rT and np.array_equal(b, rb) and np.array_equal(g, rg)
+    # two consecutive frames of one 4K stream through the whole path (state slot 3 of 4)
+    M = engine.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
+    rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    st = engine.new_state(4, S, S)
+    cal = engine.pipeline_params(squares=engine.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE), board_size=S)
+    run = engine.pipeline_params(squares=engine.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE), board_size=S)
+    engine.pipeline(f0[None], M, rects, cal, st, stream0=3)
+    T1, s1 = engine.pipeline(f1[None], M, rects, run, st, stream0=3)
+    board0 = oracle.warp(ref, M, S)
+    board1 = oracle.warp(oracle.process_pipeline(f1, True), M, S)
+    for j, (x, y, w, h) in enumerate(rects):
+        g0 = oracle.square_preprocess(board0[y:y + h, x:x + w], 5)
+        g1 = oracle.square_preprocess(board1[y:y + h, x:x + w], 5)
+        o = oracle.pd_square_stats(g1, g0)
+        m, v = oracle.cd_calibrate(g0, 100.0)
+        cnt, zmax = oracle.cd_detect(g1, m, v, 2.5)
+        r = s1[0, j]
+        assert (r["sum"], r["sumsq"], r["sad"], r["has_ref"]) == (o["sum"], o["sumsq"], o["sad"], 1)
+        assert r["cd_valid"] == 1 and r["cd_changed"] == cnt and r["cd_zmax"] == np.float32(zmax)
+    st.free()
