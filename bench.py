@@ -29,6 +29,20 @@ H, W, S = 1080, 1920, 620
 UNIQUE = 16        # distinct synthetic frames, tiled to the batch (content does not change the work)
 
 
+def measured_traffic():
+    """DRAM bytes per 1080p frame per kernel from the committed ncu capture (profiles/), or {}."""
+    best = {}
+    d = os.path.join(ROOT, "profiles")
+    if os.path.isdir(d):
+        for f in sorted(os.listdir(d)):
+            if f.endswith("_traffic.json"):
+                try:
+                    best = json.load(open(os.path.join(d, f)))
+                except Exception:
+                    pass
+    return best
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -335,10 +349,15 @@ def main():
             stages[name] = {"ms_per_launch": per_launch_ms, "share": ms / tot_ms, "launches": cnt,
                             "alg_bytes_per_launch": b, "achieved_gbs": b / per_launch_ms / 1e6,
                             "frac_of_hbm_peak": b / per_launch_ms / 1e6 / peak}
+        traffic = measured_traffic()
+        per_frame = traffic.get("dram_bytes_per_frame", {})
+        for name in stages:
+            stages[name]["traffic_bytes_per_launch"] = per_frame[name] * n if name in per_frame else None
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         d = stages[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                    "frac": d["frac_of_hbm_peak"], "traffic": d["traffic_bytes_per_launch"],
+                    "traffic_source": traffic.get("source"), "peak_source": peak_src,
                     "note": "k_fused is bound by the FP32/LSU pipes (49-tap bilateral, ~700 ops per pixel), not by HBM; "
                             "its HBM fraction is reported as the contract asks, the per-stage table gives the streaming "
                             "kernels' fractions", "stages": stages}

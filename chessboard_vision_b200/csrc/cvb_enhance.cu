@@ -315,7 +315,11 @@ struct AxisInfo {         // one per staged column / row
     float a, a1;          // blend factors
 };
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, bool FOLD = true>
+// LUTMODE: 0 = one 3 KB colour table + a multiply by the spatial weight per tap,
+//          1 = ten 3 KB tables that already hold spatial*colour (no multiply),
+//          (a third layout, 32 lane-private copies = 96 KB, removed the bank conflicts but cost a CTA per SM and was
+//          13 % slower: profiles/r01_notes.md)
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int LUTMODE = 1>
 struct FusedCfg {
     static constexpr int BX = SHARP ? 2 : 0, BY = SHARP ? 1 : 0;   // B halo around the tile
     static constexpr int BW = TW + 2 * BX, BH = TH + 2 * BY;
@@ -326,7 +330,7 @@ struct FusedCfg {
     static constexpr size_t offA = 0;
     static constexpr size_t offB = offA + (size_t)AW * AH * 4;
     static constexpr size_t offW = offB + (BIL ? (size_t)BW * BH * 4 : 0);
-    static constexpr int NLUT = FOLD ? 10 : 1;
+    static constexpr int NLUT = LUTMODE == 1 ? 10 : 1;
     static constexpr size_t offT = offW + (BIL ? NLUT * 768 * 4 : 0);
     static constexpr size_t offX = offT + (LIGHT ? sizeof(SmemColorTables) : 0);
     static constexpr size_t smem_bytes = offX + (size_t)(AW + AH) * sizeof(AxisInfo) + (size_t)(2 * TW + 2 * TH) * 2;
@@ -338,10 +342,10 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
     return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540u | (unsigned)k)) - 8388608.0f;
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, bool FOLD = true>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1>
 __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
-    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, FOLD>;
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint32_t *sA = reinterpret_cast<uint32_t *>(smem_raw + Cfg::offA);
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     if (BIL) {
         const uint4 *gw = reinterpret_cast<const uint4 *>(a.wlut);
         uint4 *dw = reinterpret_cast<uint4 *>(smem_raw + Cfg::offW);
-        for (int i = tid; i < Cfg::NLUT * 768 / 4; i += NT) dw[i] = __ldg(gw + (FOLD ? 0 : 0) + i);
+        for (int i = tid; i < Cfg::NLUT * 768 / 4; i += NT) dw[i] = __ldg(gw + i);
     }
     for (int i = tid; i < AW + AH; i += NT) {
         AxisInfo ai;
@@ -458,8 +462,9 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
                     for (int dx = -4; dx <= 4; ++dx) {
                         if (dy * dy + dx * dx > 16) continue;
                         const int c = j + 4 + dx;
-                        const float w = FOLD ? sW[r2_class(dy * dy + dx * dx) * 768 + __vsadu4(px[c], ctr[j])]
-                                             : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[__vsadu4(px[c], ctr[j])]);
+                        const unsigned sad = __vsadu4(px[c], ctr[j]);
+                        const float w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
+                                                     : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
                         wsum[j] = __fadd_rn(wsum[j], w);
                         sb[j] = __fmaf_rn(fb[c], w, sb[j]);
                         sg[j] = __fmaf_rn(fg[c], w, sg[j]);
@@ -561,11 +566,11 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     }
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, bool FOLD = true>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1>
 static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
-    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, FOLD>;
-    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, FOLD>;
+    using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE>;
     static bool attr_done = false;
     if (!attr_done) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
@@ -613,10 +618,10 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
     // Tile shapes measured on B200 at 1080p (profiles/r01_notes.md): 120x60 outputs per 512-thread CTA tile 1080p and
     // 4K exactly and keep the halo overheads low (B 1.10x, A 1.28x); the folded 30 KB weight table beat the 3 KB one.
-    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, true>(h, a, n);
-    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, true>(h, a, n);
-    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, true>(h, a, n);
-    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, true>(h, a, n);
+    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, 1>(h, a, n);
+    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, 1>(h, a, n);
+    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, 1>(h, a, n);
+    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, 1>(h, a, n);
     if (!light && !bilateral && sharpen) return launch_fused_t<60, 30, false, false, true>(h, a, n);
     if (light && !bilateral && !sharpen) return launch_fused_t<60, 30, true, false, false>(h, a, n);
     cvb_set_error("unsupported fused stage combination");

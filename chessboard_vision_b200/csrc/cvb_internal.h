@@ -69,7 +69,7 @@ struct cvb_handle {
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    int chunk_frames = 16;
+    int chunk_frames = 8;
     // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
     DevBuf ws_masks;
     void *pinned = nullptr;

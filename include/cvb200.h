@@ -240,7 +240,7 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                      uint8_t *warped, cvb_square_stats *stats);
 /* host-buffer variant (the call the Python shim times as "e2e"): bgr HOST
  * (pinned or pageable) in; stats / otsu_t HOST out.  The batch is processed
- * in chunks of cvb_set_chunk_frames() frames (default 16): the host->device
+ * in chunks of cvb_set_chunk_frames() frames (default 8): the host->device
  * copy of chunk k+1 overlaps the kernels of chunk k when bgr is page-locked. */
 int cvb_set_chunk_frames(cvb_handle *h, int frames);
 int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
