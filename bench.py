@@ -123,7 +123,9 @@ def make_pool(frames):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in loop mode, started before the warm-up so that it is already sampling when the timed
+    region begins; only the samples whose timestamp falls inside the timed region are summarised."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -132,49 +134,65 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def wait_ready(self, timeout=3.0):
+        """Block until the first sample has been written (nvidia-smi takes a few 100 ms to start)."""
+        t = time.time()
+        while self.p is not None and time.time() - t < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
+    def stop(self, t0, t1):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), c[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         self.f.close()
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
-        if sm:
-            # under load = the upper half of the samples (the sampler also sees the idle edges)
-            hi = sorted(sm)[len(sm) // 2:]
-            out.update(sm_mhz=float(np.median(hi)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t0 <= r[0] <= t1] or [r for r in rows if t0 - 0.3 <= r[0] <= t1 + 0.3]
+        if inside:
+            reasons = set()
+            for r in inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted(reasons), samples=len(inside))
         return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
@@ -317,10 +335,14 @@ def main():
             ms = float(t.item())
         return ms, launches
 
-    run_dev(args.warmup)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_ready()
+    run_dev(args.warmup)
+    wall0 = time.time()
     ms_dev, launches = timed(run_dev, args.steps)
-    clocks = sampler.stop() if sampler else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if sampler else None
 
     # per-kernel device time (CUDA events around every launch, same K steps) -> roofline of the dominant kernel
     eng.profile(True)
