@@ -269,7 +269,11 @@ int cvb_get_tables(uint16_t *gamma256, uint16_t *cbrt2048, int32_t *lab2yf512, u
     const CvbTables &t = cvb_host_tables();
     if (gamma256) memcpy(gamma256, t.gamma, sizeof t.gamma);
     if (cbrt2048) memcpy(cbrt2048, t.cbrt, sizeof t.cbrt);
-    if (lab2yf512) memcpy(lab2yf512, t.lab2yf, sizeof t.lab2yf);
+    if (lab2yf512)      // public layout: (y, ify) pairs as in OpenCV's LabToYF_b; the kernels keep them packed
+        for (int L = 0; L < 256; ++L) {
+            lab2yf512[2 * L] = t.lab2yf[L] & 0xffff;
+            lab2yf512[2 * L + 1] = (int32_t)((uint32_t)t.lab2yf[L] >> 16);
+        }
     if (invgamma4096) memcpy(invgamma4096, t.invgamma, sizeof t.invgamma);
     if (ltab2048) memcpy(ltab2048, t.ltab, sizeof t.ltab);
     return CVB_OK;

@@ -21,7 +21,7 @@ CVB_DEV uint32_t pack_bgr(int b, int g, int r) { return (uint32_t)b | ((uint32_t
 struct __align__(16) SmemColorTables {
     uint16_t gamma[256];
     uint16_t cbrt[2048];
-    int32_t  lab2yf[512];
+    int32_t  lab2yf[512];      // [0..255]: y | ify << 16 (one load per pixel); [256..511] unused padding
     uint8_t  invgamma[4096];
 };
 static_assert(sizeof(SmemColorTables) % 16 == 0, "vector copy");
@@ -56,7 +56,8 @@ CVB_DEV int ab_to_xz(int t)
 // S3: Lab2RGBinteger (8-bit) -- reference call frame_enhancer.py:120
 CVB_DEV uint32_t lab2bgr_px(const SmemColorTables *t, int L, int a, int b)
 {
-    const int y = t->lab2yf[2 * L], ify = t->lab2yf[2 * L + 1];
+    const uint32_t yf = (uint32_t)t->lab2yf[L];          // both values are < 2^15
+    const int y = yf & 0xffff, ify = yf >> 16;
     const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
     const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
     const int x = ab_to_xz(ify + adiv), z = ab_to_xz(ify - bdiv);

@@ -309,16 +309,11 @@ __host__ __device__ constexpr int r2_class(int r2)
 }
 static const int kR2[10] = {0, 1, 2, 4, 5, 8, 9, 10, 13, 16};
 
-struct AxisInfo {         // one per staged column / row
-    int src;              // mirrored source coordinate
-    int o1, o2;           // CLAHE LUT offsets of the two neighbouring tiles (already * 256 [* tiles_x])
-    float a, a1;          // blend factors
+struct __align__(8) AxisInfo {   // one per staged column / row: a single 64-bit shared load
+    float a;                     // CLAHE blend factor towards the second tile (a1 = 1 - a)
+    uint32_t packed;             // mirrored source coordinate (low 16) | first tile index << 16 | second << 24
 };
 
-// LUTMODE: 0 = one 3 KB colour table + a multiply by the spatial weight per tap,
-//          1 = ten 3 KB tables that already hold spatial*colour (no multiply),
-//          (a third layout, 32 lane-private copies = 96 KB, removed the bank conflicts but cost a CTA per SM and was
-//          13 % slower: profiles/r01_notes.md)
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int LUTMODE = 1>
 struct FusedCfg {
     static constexpr int BX = SHARP ? 2 : 0, BY = SHARP ? 1 : 0;   // B halo around the tile
@@ -342,6 +337,9 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
     return __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7540u | (unsigned)k)) - 8388608.0f;
 }
 
+#ifndef CONV_MIX
+#define CONV_MIX 1
+#endif
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1>
 __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
@@ -371,11 +369,12 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         AxisInfo ai;
         const bool col = i < AW;
         const int p = col ? reflect101(ax0 + i, W) : reflect101(ay0 + (i - AW), H);
-        ai.src = p; ai.o1 = ai.o2 = 0; ai.a = ai.a1 = 0.f;
+        ai.a = 0.f;
+        ai.packed = (uint32_t)p;
         if (LIGHT) {
             const ClaheAxis ca = col ? clahe_axis(p, a.g.inv_tw, a.g.tiles_x) : clahe_axis(p, a.g.inv_th, a.g.tiles_y);
-            const int mul = col ? 256 : 256 * a.g.tiles_x;
-            ai.o1 = ca.i1 * mul; ai.o2 = ca.i2 * mul; ai.a = ca.a; ai.a1 = ca.a1;
+            ai.a = ca.a;
+            ai.packed |= ((uint32_t)ca.i1 << 16) | ((uint32_t)ca.i2 << 24);
         }
         sAx[i] = ai;
     }
@@ -399,17 +398,21 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         for (int i = tid; i < AW * AH; i += NT) {
             const int ly = i / AW, lx = i - ly * AW;
             const AxisInfo cx = sAx[lx], cy = sAx[AW + ly];
-            const uint8_t *p = img + ((size_t)cy.src * W + cx.src) * 3;
+            const int sx = cx.packed & 0xffff, sy = cy.packed & 0xffff;
+            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
             const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
             uint32_t q;
             if (LIGHT) {
                 int L, A, B;
                 bgr2lab_px(sTab, c0, c1, c2, L, A, B);
-                const uint8_t *l1 = lut + cy.o1 + L, *l2 = lut + cy.o2 + L;
-                const float l11 = (float)__ldg(l1 + cx.o1), l12 = (float)__ldg(l1 + cx.o2);
-                const float l21 = (float)__ldg(l2 + cx.o1), l22 = (float)__ldg(l2 + cx.o2);
-                const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, cx.a1), __fmul_rn(l12, cx.a)), cy.a1);
-                const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, cx.a1), __fmul_rn(l22, cx.a)), cy.a);
+                const int tx1 = (cx.packed >> 16) & 0xff, tx2 = cx.packed >> 24;
+                const uint8_t *l1 = lut + (((cy.packed >> 16) & 0xff) * a.g.tiles_x << 8) + L;
+                const uint8_t *l2 = lut + ((cy.packed >> 24) * a.g.tiles_x << 8) + L;
+                const float l11 = (float)__ldg(l1 + (tx1 << 8)), l12 = (float)__ldg(l1 + (tx2 << 8));
+                const float l21 = (float)__ldg(l2 + (tx1 << 8)), l22 = (float)__ldg(l2 + (tx2 << 8));
+                const float xa1 = __fsub_rn(1.0f, cx.a), ya1 = __fsub_rn(1.0f, cy.a);
+                const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, cx.a)), ya1);
+                const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, cx.a)), cy.a);
                 L = round_u8(__fadd_rn(top, bot));
                 q = lab2bgr_px(sTab, L, A, B);
             } else {
@@ -454,7 +457,8 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
                     if (c < lo || c > 11 - lo) continue;
                     fb[c] = byte_to_float(px[c], 0);
                     fg[c] = byte_to_float(px[c], 1);
-                    fr[c] = byte_to_float(px[c], 2);
+                    // one channel goes through the otherwise idle conversion unit (I2F.U8): one issue slot instead of two
+                    fr[c] = CONV_MIX ? (float)((px[c] >> 16) & 0xffu) : byte_to_float(px[c], 2);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

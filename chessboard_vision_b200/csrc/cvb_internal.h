@@ -32,7 +32,7 @@ void cvb_set_error(const char *fmt, ...);
 struct CvbTables {
     uint16_t gamma[256];       // sRGBGammaTab_b
     uint16_t cbrt[2048];       // LabCbrtTab_b, index <= 2040 reachable
-    int32_t  lab2yf[512];      // LabToYF_b (y, ify)
+    int32_t  lab2yf[512];      // LabToYF_b: [L] = y | ify << 16 for L < 256, rest padding
     uint8_t  invgamma[4096];   // sRGBInvGammaTab_b
     uint8_t  ltab[2048];       // L as a function of the Y index (histogram pass)
 };

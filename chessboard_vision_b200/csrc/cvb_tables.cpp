@@ -45,8 +45,9 @@ void build_tables()
             ify = std::nearbyint(fy);
             y = std::nearbyint(fy * fy * fy / (base * base));
         }
-        t.lab2yf[2 * L] = (int32_t)y;
-        t.lab2yf[2 * L + 1] = (int32_t)ify;
+        // kernel layout: y in the low half-word, ify in the high one (both < 2^15)
+        t.lab2yf[L] = (int32_t)y | ((int32_t)ify << 16);
+        t.lab2yf[256 + L] = 0;
     }
     for (int i = 0; i < 4096; ++i) {
         int v = (int)std::nearbyint(255.0 * gamma_inv(i / 4096.0));
