@@ -11,6 +11,7 @@ GPU; weak scaling: every rank owns its own 256 frames and its own per-stream
 state, no data-path collective).  Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -199,6 +200,7 @@ def main():
     ap.add_argument("--kind", default="board", choices=["board", "noise"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0: 4 per host core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-frame latency / config-3 side measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -276,7 +278,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from chessboard_vision_b200.engine import (Engine, grid_rects, STATS_DTYPE, SQ_PD_STATS, SQ_PD_SET_REF,
+    from chessboard_vision_b200.engine import (Engine, grid_rects, _rect_array, STATS_DTYPE, SQ_PD_STATS, SQ_PD_SET_REF,
                                                SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
     eng = Engine(local_rank)
     n = args.frames
@@ -353,6 +355,48 @@ def main():
     run_e2e(args.warmup)
     ms_e2e, _ = timed(run_e2e, args.steps)
 
+    # ---- side measurements for the other BASELINE.json configs (rank 0, not part of value/e2e) ----
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        one = eng.empty((1, H, W, 3))
+        eng.lib.cvb_memcpy_h2d(eng.h, one.ptr, host.ctypes.data, H * W * 3)
+        st1 = eng.new_state(1, S, S)
+        s1 = eng.empty((1, len(rects)), STATS_DTYPE); o1 = eng.empty((1,), np.int32)
+        eng.pipeline_dev(one, M, rects, pp_cal, st1, stats=s1, otsu_t=o1)
+        lat = []
+        for _ in range(25):
+            e0, e1 = eng.event(), eng.event()
+            eng.record(e0); eng.pipeline_dev(one, M, rects, pp, st1, stats=s1, otsu_t=o1); eng.record(e1)
+            lat.append(eng.elapsed_ms(e0, e1))
+        lat_host = []
+        for _ in range(25):
+            t0 = time.perf_counter(); eng.pipeline(host[:1], M, rects, pp, st1); lat_host.append((time.perf_counter() - t0) * 1e3)
+        extras["config2_single_1080p_frame"] = {"device_ms_median": float(np.median(lat[5:])),
+                                                "host_call_ms_median": float(np.median(lat_host[5:])),
+                                                "what": "enhance + analysis + warp + 64 squares + statistics, one frame"}
+        # config 3: per-square change statistics on 64 consecutive-frame pairs (warp + square kernel only)
+        nb = 64
+        boards_in = eng.empty((nb, H, W, 3))
+        eng.lib.cvb_memcpy_h2d(eng.h, boards_in.ptr, host.ctypes.data, nb * H * W * 3)
+        warped = eng.empty((nb, S, S, 3)); st3 = eng.new_state(nb, S, S); s3 = eng.empty((nb, len(rects)), STATS_DTYPE)
+        eng.lib.cvb_warp_dev(eng.h, boards_in.ptr, nb, H, W, M.ctypes.data, 1, S, S, warped.ptr)
+        eng.squares(warped, rects, sq_cal, st3, want_stats=False)
+        rect_arr = _rect_array(rects)
+        e0, e1 = eng.event(), eng.event()
+        eng.record(e0)
+        for _ in range(10):
+            eng.lib.cvb_warp_dev(eng.h, boards_in.ptr, nb, H, W, M.ctypes.data, 1, S, S, warped.ptr)
+            eng.lib.cvb_squares_dev(eng.h, warped.ptr, nb, S, S, 3, ctypes.cast(rect_arr, ctypes.c_void_p),
+                                    len(rects), None, st3.ptr, 0, ctypes.byref(sq_run), s3.ptr)
+        eng.record(e1)
+        ms3 = eng.elapsed_ms(e0, e1) / 10
+        extras["config3_change_stats_64_pairs"] = {"ms_per_batch": ms3, "frames_per_s": nb / ms3 * 1e3,
+                                                   "what": "warp + 64 squares: absdiff delta, moments, centre/border, rings, "
+                                                           "z-score detect + EMA update (resident inputs)"}
+        for x in (one, s1, o1, boards_in, warped, s3):
+            x.free()
+        st1.free(); st3.free()
+
     total_frames = n * args.steps * world
     value = total_frames / (ms_dev / 1e3)
     e2e = total_frames / (ms_e2e / 1e3)
@@ -397,7 +441,8 @@ def main():
                        "ms_per_step": ms_e2e / args.steps,
                        "api": "Engine.pipeline -> cvb_pipeline (pinned host frames in, per-square statistics + Otsu "
                               "thresholds out)"},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+               "extras": extras}
         emit(out)
     if dist is not None:
         dist.destroy_process_group()

@@ -964,32 +964,54 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) k_otsu(const int32_t *__restrict__ hist, long npx, int32_t *__restrict__ otsu_t)
 {
-    __shared__ double s_p[256];
+    // Only the (q1, mu1) recurrence is sequential; p_i, i*p_i and mu before it, and mu2 / sigma / arg-max
+    // after it, are spread over the warp.  Every operation keeps OpenCV's operands and rounding.
+    __shared__ double s_p[256], s_ip[256], s_q1[256], s_mu1[256];
+    __shared__ unsigned char s_ok[256];
     const int frame = blockIdx.x, lane = threadIdx.x;
     const int32_t *hh = hist + (size_t)frame * 256;
     const double scale = __ddiv_rn(1.0, (double)npx);
-    for (int i = lane; i < 256; i += 32) s_p[i] = __dmul_rn((double)hh[i], scale);
+    double part = 0;     // sum of i*h[i]: integers below 2^53, exact in any order
+    for (int i = lane; i < 256; i += 32) {
+        const double hv = (double)hh[i];
+        const double p = __dmul_rn(hv, scale);
+        s_p[i] = p;
+        s_ip[i] = __dmul_rn((double)i, p);
+        part += __dmul_rn((double)i, hv);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const double mu = __dmul_rn(part, scale);
     __syncwarp();
     if (lane == 0) {
-        double mu = 0;
-        for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)hh[i]));
-        mu = __dmul_rn(mu, scale);
-        double mu1 = 0, q1 = 0, max_sigma = 0;
-        int max_val = 0;
+        double mu1 = 0, q1 = 0;
         for (int i = 0; i < 256; ++i) {
-            const double p_i = s_p[i];
             mu1 = __dmul_rn(mu1, q1);
-            q1 = __dadd_rn(q1, p_i);
+            q1 = __dadd_rn(q1, s_p[i]);
             const double q2 = __dsub_rn(1.0, q1);
-            if (fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON) continue;
-            mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
-            const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
-            const double d = __dsub_rn(mu1, mu2);
-            const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
-            if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+            const bool ok = !(fmin(q1, q2) < (double)FLT_EPSILON || fmax(q1, q2) > 1.0 - (double)FLT_EPSILON);
+            if (ok) mu1 = __ddiv_rn(__dadd_rn(mu1, s_ip[i]), q1);
+            s_q1[i] = q1; s_mu1[i] = mu1; s_ok[i] = ok;
         }
-        otsu_t[frame] = max_val;
     }
+    __syncwarp();
+    double best = 0;      // `sigma > max_sigma` with max_sigma starting at 0: the first strict maximum wins
+    int best_i = 0;
+    for (int i = lane; i < 256; i += 32) {
+        if (!s_ok[i]) continue;
+        const double q1 = s_q1[i], mu1 = s_mu1[i], q2 = __dsub_rn(1.0, q1);
+        const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+        const double d = __dsub_rn(mu1, mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), d), d);
+        if (sigma > best) { best = sigma; best_i = i; }      // ascending i per lane: first maximum of the lane
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob > best || (ob == best && ob > 0 && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) otsu_t[frame] = best > 0 ? best_i : 0;
 }
 int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t)
 {
