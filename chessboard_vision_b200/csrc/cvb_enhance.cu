@@ -340,7 +340,7 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
 #ifndef CONV_MIX
 #define CONV_MIX 1
 #endif
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
 __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
@@ -424,28 +424,38 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     __syncthreads();
 
     // ---- B ----
+    // ROWS output rows per thread: a window row is loaded and converted to float once and feeds every output
+    // row of the thread it is in range of (ROWS == 2 halves the byte->float conversions and the LDS.128s).
     if (BIL) {
         constexpr int RUNS = Cfg::RUNS;
-        for (int item = tid; item < BH * RUNS; item += NT) {
-            const int row = item / RUNS, r4 = (item - row * RUNS) * 4;
-            const int Y = by0 + row, X = bx0 + r4;
-            if (Y < 0 || Y >= H || X + 3 < 0 || X >= W) continue;
-            float wsum[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f},
-                  sr[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t ctr[4];
-            {
-                const uint4 c = *reinterpret_cast<const uint4 *>(sA + (row + 4) * AW + r4 + 4);
-                ctr[0] = c.x; ctr[1] = c.y; ctr[2] = c.z; ctr[3] = c.w;
+        static_assert(BH % ROWS == 0, "B rows must split evenly over the rows of a thread");
+        for (int item = tid; item < (BH / ROWS) * RUNS; item += NT) {
+            const int rg = item / RUNS, r4 = (item - rg * RUNS) * 4;
+            const int row0 = rg * ROWS;
+            const int Y0 = by0 + row0, X = bx0 + r4;
+            if (Y0 + ROWS - 1 < 0 || Y0 >= H || X + 3 < 0 || X >= W) continue;
+            float wsum[ROWS][4], sb[ROWS][4], sg[ROWS][4], sr[ROWS][4];
+            uint32_t ctr[ROWS][4];
+#pragma unroll
+            for (int t = 0; t < ROWS; ++t) {
+                const uint4 c = *reinterpret_cast<const uint4 *>(sA + (row0 + t + 4) * AW + r4 + 4);
+                ctr[t][0] = c.x; ctr[t][1] = c.y; ctr[t][2] = c.z; ctr[t][3] = c.w;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wsum[t][j] = sb[t][j] = sg[t][j] = sr[t][j] = 0.f;
             }
 #pragma unroll
-            for (int dy = -4; dy <= 4; ++dy) {
-                const uint32_t *rowp = sA + (row + 4 + dy) * AW + r4;
+            for (int k = 0; k < 9 + ROWS - 1; ++k) {          // window row k is A row (row0 + k): dy = k - 4 - t for output row t
+                const uint32_t *rowp = sA + (row0 + k) * AW + r4;
                 uint32_t px[12];
                 float fb[12], fg[12], fr[12];
-                // columns r4 .. r4+11 of the A tile hold image x = X-4 .. X+7;
-                // first needed column: 4 - (largest |dx| on this row of the disc)
-                const int ady = dy < 0 ? -dy : dy;
-                const int lo = ady == 4 ? 4 : ady == 3 ? 2 : ady >= 1 ? 1 : 0;
+                // columns r4 .. r4+11 of the A tile hold image x = X-4 .. X+7; first needed column over the rows fed:
+                // 4 - (largest |dx| of the disc on that dy)
+                int lo = 4;
+#pragma unroll
+                for (int t = 0; t < ROWS; ++t) {
+                    const int dy = k - 4 - t, ady = dy < 0 ? -dy : dy;
+                    if (ady <= 4) lo = min(lo, ady == 4 ? 4 : ady == 3 ? 2 : ady >= 1 ? 1 : 0);
+                }
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
                     if (v != 1 && lo >= 4) continue;                 // |dy| == 4 needs only the middle quad
@@ -461,30 +471,38 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
                     fr[c] = CONV_MIX ? (float)((px[c] >> 16) & 0xffu) : byte_to_float(px[c], 2);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int t = 0; t < ROWS; ++t) {
+                    const int dy = k - 4 - t;
+                    if (dy < -4 || dy > 4) continue;
 #pragma unroll
-                    for (int dx = -4; dx <= 4; ++dx) {
-                        if (dy * dy + dx * dx > 16) continue;
-                        const int c = j + 4 + dx;
-                        const unsigned sad = __vsadu4(px[c], ctr[j]);
-                        const float w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
-                                                     : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
-                        wsum[j] = __fadd_rn(wsum[j], w);
-                        sb[j] = __fmaf_rn(fb[c], w, sb[j]);
-                        sg[j] = __fmaf_rn(fg[c], w, sg[j]);
-                        sr[j] = __fmaf_rn(fr[c], w, sr[j]);
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int dx = -4; dx <= 4; ++dx) {
+                            if (dy * dy + dx * dx > 16) continue;
+                            const int c = j + 4 + dx;
+                            const unsigned sad = __vsadu4(px[c], ctr[t][j]);
+                            const float w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
+                                                         : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
+                            wsum[t][j] = __fadd_rn(wsum[t][j], w);
+                            sb[t][j] = __fmaf_rn(fb[c], w, sb[t][j]);
+                            sg[t][j] = __fmaf_rn(fg[c], w, sg[t][j]);
+                            sr[t][j] = __fmaf_rn(fr[c], w, sr[t][j]);
+                        }
                     }
                 }
             }
-            uint4 o;
-            uint32_t *op = &o.x;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float inv = __fdiv_rn(1.0f, wsum[j]);
-                op[j] = pack_bgr(round_u8(__fmul_rn(sb[j], inv)), round_u8(__fmul_rn(sg[j], inv)),
-                                 round_u8(__fmul_rn(sr[j], inv)));
+            for (int t = 0; t < ROWS; ++t) {
+                uint4 o;
+                uint32_t *op = &o.x;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float inv = __fdiv_rn(1.0f, wsum[t][j]);
+                    op[j] = pack_bgr(round_u8(__fmul_rn(sb[t][j], inv)), round_u8(__fmul_rn(sg[t][j], inv)),
+                                     round_u8(__fmul_rn(sr[t][j], inv)));
+                }
+                *reinterpret_cast<uint4 *>(sB + (row0 + t) * BW + r4) = o;
             }
-            *reinterpret_cast<uint4 *>(sB + row * BW + r4) = o;
         }
         __syncthreads();
     }
@@ -570,11 +588,11 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     }
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
 static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
-    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS>;
     static bool attr_done = false;
     if (!attr_done) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
@@ -622,10 +640,10 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
     // Tile shapes measured on B200 at 1080p (profiles/r01_notes.md): 120x60 outputs per 512-thread CTA tile 1080p and
     // 4K exactly and keep the halo overheads low (B 1.10x, A 1.28x); the folded 30 KB weight table beat the 3 KB one.
-    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, 1>(h, a, n);
-    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, 1>(h, a, n);
-    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, 1>(h, a, n);
-    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, 1>(h, a, n);
+    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, 1, 2>(h, a, n);
+    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, 1, 2>(h, a, n);
+    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, 1, 2>(h, a, n);
+    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, 1, 2>(h, a, n);
     if (!light && !bilateral && sharpen) return launch_fused_t<60, 30, false, false, true>(h, a, n);
     if (light && !bilateral && !sharpen) return launch_fused_t<60, 30, true, false, false>(h, a, n);
     cvb_set_error("unsupported fused stage combination");
