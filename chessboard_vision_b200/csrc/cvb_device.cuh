@@ -94,6 +94,21 @@ CVB_DEV int clahe_interp(const uint8_t *__restrict__ lut, int tiles_x, const Cla
 
 // S7: RGB2Gray<uchar>, 15-bit coefficients -- frame_enhancer.py:154
 CVB_DEV int gray_px(int b, int g, int r) { return (3735 * b + 19235 * g + 9798 * r + 16384) >> 15; }
+// the same on a packed (b, g, r, x) word: two 16x8-bit dot products (IDP.2A), no byte extraction
+CVB_DEV unsigned gray_packed(uint32_t bgrx)
+{
+    const unsigned bg = __dp2a_lo(3735u | (19235u << 16), bgrx, 16384u);
+    return __dp2a_hi(9798u, bgrx, bg) >> 15;
+}
+// gray of the four pixels held in three consecutive words (b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3), packed
+CVB_DEV uint32_t gray4_from_words(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const unsigned g0 = gray_packed(w0);
+    const unsigned g1 = gray_packed(__byte_perm(w0, w1, 0x6543));
+    const unsigned g2 = gray_packed(__byte_perm(w1, w2, 0x5432));
+    const unsigned g3 = gray_packed(w2 >> 8);
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
 
 // S6: the 256-entry map of cv2.normalize(NORM_MINMAX,0,255) for one (min,max):
 // f64 scale/shift, then f32 fma per value (convert_scale.simd.hpp, FMA3 hosts)

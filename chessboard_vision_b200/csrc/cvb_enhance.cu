@@ -799,29 +799,31 @@ int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 128x32, halo 2.
-//   1  groups of 4 pixels (three 32-bit words) straight from the sharpened frame:
-//      min-max map (skipped when it is the identity), write the enhanced pixels (3 words)
-//      and gray (1 word), keep gray (+ halo) in shared memory;
+// Pass 3: normalize -> gray -> blur5 -> histogram.  Tile 120x36 (tiles 1080p and 4K exactly), halo 2.
+//   Thread mapping: a warp owns a row, a lane owns a group of 4 pixels (120 + 2*4 columns = 32 groups),
+//   so row pointers are warp-uniform and a warp moves 384 contiguous bytes per row.
+//   1  groups of 4 pixels (three 32-bit words) straight from the sharpened frame: min-max map
+//      (skipped when it is the identity), write the enhanced pixels (3 words) and gray (1 word),
+//      keep gray (+ halo) in shared memory;
 //   2  horizontal [1 4 6 4 1];  3  vertical [1 4 6 4 1], (sum+128)>>8, histogram.
 // Mirror rows / columns (REFLECT_101 of GaussianBlur) are resolved when gray is staged.
+// FAST: W % 4 == 0 and every pointer 4-byte aligned, so a group is three aligned words and never
+// straddles the right image edge; the generic instance keeps the byte paths.
 // ---------------------------------------------------------------------------------------
-template <bool NORM>
+template <bool NORM, bool FAST>
 __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src, int H, int W,
                                                 const int32_t *__restrict__ minmax, uint8_t *__restrict__ enhanced,
                                                 uint8_t *__restrict__ gray, uint8_t *__restrict__ blurred,
                                                 int32_t *__restrict__ hist)
 {
-    constexpr int FW = 128, FH = 32, R = 2, PADX = 4;
-    constexpr int GH = FH + 2 * R;                 // staged rows
-    constexpr int SW = FW + 2 * PADX;              // gray columns: X = x0-4 .. x0+131
-    constexpr int NG = SW / 4;                     // 34 groups per row
+    constexpr int FW = 120, FH = 36, R = 2, PADX = 4;
+    constexpr int GH = FH + 2 * R;                 // 40 staged rows: 5 per warp
+    constexpr int SW = FW + 2 * PADX;              // 128 gray columns: X = x0-4 .. x0+123, 32 groups
     __shared__ __align__(16) uint8_t s_g[GH][SW];
     __shared__ __align__(8) uint16_t s_h[GH][FW];
     __shared__ int s_hist[8][256];
     __shared__ uint8_t s_map[256];
-    __shared__ int s_rowofs[GH];                   // mirrored source row of each staged row
-    const int tid = threadIdx.x, frame = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.z;
     const int x0 = blockIdx.x * FW, y0 = blockIdx.y * FH;
     const size_t fo = (size_t)frame * H * W;
     const uint8_t *img = src + fo * 3;
@@ -832,22 +834,22 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
         const int lo = minmax[2 * frame], hi = minmax[2 * frame + 1];
         identity = (lo == 0 && hi == 255);
         if (!identity) s_map[tid] = (uint8_t)normalize_value(tid, lo, hi);
+        __syncthreads();
     }
-    if (tid < GH) s_rowofs[tid] = reflect101(y0 - R + tid, H);
-    __syncthreads();
     // ---- 1 ----
-    const bool al4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
-    const bool out4 = al4 && ((reinterpret_cast<uintptr_t>(enhanced) & 3) == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0);
-    for (int item = tid; item < GH * NG; item += 256) {
-        const int ly = item / NG, gi = item - ly * NG;
-        const int X = x0 - PADX + 4 * gi;
-        const int sy = s_rowofs[ly];
+    const int X = x0 - PADX + 4 * lane;            // first pixel of this lane's group
+    const bool inside = X >= 0 && X + 3 < W;
+    const bool interior_col = lane >= 1 && lane <= FW / 4 && X < W;
+    for (int ly = warp; ly < GH; ly += 8) {
+        const int Y = y0 - R + ly;
+        const int sy = reflect101(Y, H);
         const uint8_t *rowp = img + (size_t)sy * W * 3;
+        const bool interior = interior_col && ly >= R && ly < GH - R && Y < H;
         uint32_t gpack = 0;
-        if (X >= 0 && X + 3 < W) {
+        if (inside) {
             const uint8_t *p = rowp + (size_t)X * 3;
             uint32_t w0, w1, w2;
-            if (al4) {
+            if (FAST) {
                 const uint32_t *p32 = reinterpret_cast<const uint32_t *>(p);
                 w0 = __ldg(p32); w1 = __ldg(p32 + 1); w2 = __ldg(p32 + 2);
             } else {
@@ -860,18 +862,12 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                 w1 = s_map[w1 & 0xff] | (s_map[(w1 >> 8) & 0xff] << 8) | (s_map[(w1 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w1 >> 24] << 24);
                 w2 = s_map[w2 & 0xff] | (s_map[(w2 >> 8) & 0xff] << 8) | (s_map[(w2 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w2 >> 24] << 24);
             }
-            // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-            const int g0 = gray_px(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
-            const int g1 = gray_px(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
-            const int g2 = gray_px((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
-            const int g3 = gray_px((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
-            gpack = (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)g2 << 16) | ((uint32_t)g3 << 24);
-            const int Y = y0 - R + ly;
-            if (ly >= R && ly < GH - R && Y < H && gi >= 1 && gi <= FW / 4) {   // interior of this tile
+            gpack = gray4_from_words(w0, w1, w2);
+            if (interior) {
                 const size_t po = (size_t)Y * W + X;
                 if (enhanced) {
                     uint8_t *o = enhanced + (fo + po) * 3;
-                    if (out4) {
+                    if (FAST) {
                         uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
                         o32[0] = w0; o32[1] = w1; o32[2] = w2;
                     } else {
@@ -881,14 +877,13 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                 }
                 if (gray) {
                     uint8_t *o = gray + fo + po;
-                    if (out4) *reinterpret_cast<uint32_t *>(o) = gpack;
+                    if (FAST) *reinterpret_cast<uint32_t *>(o) = gpack;
                     else
                         for (int i = 0; i < 4; ++i) o[i] = (uint8_t)(gpack >> (8 * i));
                 }
             }
         } else {
-            // group touching an image edge: per pixel, with mirrored columns
-            const int Y = y0 - R + ly;
+            // group touching / beyond an image edge: per pixel, with mirrored columns
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int Xj = X + j;
@@ -908,51 +903,58 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                 }
             }
         }
-        *reinterpret_cast<uint32_t *>(&s_g[ly][4 * gi]) = gpack;
+        *reinterpret_cast<uint32_t *>(&s_g[ly][4 * lane]) = gpack;
     }
     __syncthreads();
-    // ---- 2: horizontal pass, 4 outputs per item (output x <-> gray columns x+2 .. x+6) ----
-    for (int item = tid; item < GH * (FW / 4); item += 256) {
-        const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
-        const uint32_t *gp = reinterpret_cast<const uint32_t *>(&s_g[ly][x]);
-        const uint32_t a = gp[0], b = gp[1], c = gp[2];          // columns x .. x+11
-        const int v2 = (a >> 16) & 0xff, v3 = a >> 24, v4 = b & 0xff, v5 = (b >> 8) & 0xff, v6 = (b >> 16) & 0xff,
-                  v7 = b >> 24, v8 = c & 0xff, v9 = (c >> 8) & 0xff;
-        const uint32_t h0 = v2 + 4 * v3 + 6 * v4 + 4 * v5 + v6, h1 = v3 + 4 * v4 + 6 * v5 + 4 * v6 + v7;
-        const uint32_t h2 = v4 + 4 * v5 + 6 * v6 + 4 * v7 + v8, h3 = v5 + 4 * v6 + 6 * v7 + 4 * v8 + v9;
-        *reinterpret_cast<uint2 *>(&s_h[ly][x]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    // ---- 2: horizontal pass, 4 outputs per lane (output x <-> gray columns x+2 .. x+6), lanes 0..29 ----
+    if (lane < FW / 4) {
+        const int x = 4 * lane;
+        for (int ly = warp; ly < GH; ly += 8) {
+            const uint32_t *gp = reinterpret_cast<const uint32_t *>(&s_g[ly][x]);
+            const uint32_t a = gp[0], b = gp[1], c = gp[2];          // columns x .. x+11
+            // h_k = v[k+2] + 4 v[k+3] + 6 v[k+4] + 4 v[k+5] + v[k+6]: one 4x8-bit dot product (weights 1,4,6,4) + the fifth tap
+            constexpr uint32_t kW = 1u | (4u << 8) | (6u << 16) | (4u << 24);
+            const uint32_t h0 = __dp4a(__byte_perm(a, b, 0x5432), kW, (b >> 16) & 0xffu);
+            const uint32_t h1 = __dp4a(__byte_perm(a, b, 0x6543), kW, b >> 24);
+            const uint32_t h2 = __dp4a(b, kW, c & 0xffu);
+            const uint32_t h3 = __dp4a(__byte_perm(b, c, 0x4321), kW, (c >> 8) & 0xffu);
+            *reinterpret_cast<uint2 *>(&s_h[ly][x]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+        }
     }
     __syncthreads();
     // ---- 3: vertical pass + histogram ----
-    int *myh = s_hist[tid >> 5];
-    const bool b4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(blurred) & 3) == 0);
-    for (int item = tid; item < FH * (FW / 4); item += 256) {
-        const int ly = item / (FW / 4), x = (item - ly * (FW / 4)) * 4;
-        const int Y = y0 + ly, X = x0 + x;
-        if (Y >= H || X >= W) continue;
-        const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
-        const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
-        const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
-        const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
-        const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
-        // two 16-bit lanes per word; each lane's sum is <= 255*256 = 65280, so no carry crosses lanes
-        const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
-        const uint32_t hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
-        const int o0 = ((lo & 0xffff) + 128) >> 8, o1 = ((lo >> 16) + 128) >> 8;
-        const int o2 = ((hi & 0xffff) + 128) >> 8, o3 = ((hi >> 16) + 128) >> 8;
-        const int ov[4] = {o0, o1, o2, o3};
-        const int nvalid = min(4, W - X);
-        if (hist) {
+    int *myh = s_hist[warp];
+    if (lane < FW / 4) {
+        const int x = 4 * lane, Xo = x0 + x;
+        if (Xo < W) {
+            const int nvalid = FAST ? 4 : min(4, W - Xo);
+            for (int ly = warp; ly < FH; ly += 8) {
+                const int Y = y0 + ly;
+                if (Y >= H) break;
+                const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
+                const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
+                const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
+                const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
+                const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
+                // two 16-bit lanes per word; each lane's sum is <= 255*256 = 65280, so no carry crosses lanes
+                const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
+                const uint32_t hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
+                const int o0 = ((lo & 0xffff) + 128) >> 8, o1 = ((lo >> 16) + 128) >> 8;
+                const int o2 = ((hi & 0xffff) + 128) >> 8, o3 = ((hi >> 16) + 128) >> 8;
+                const int ov[4] = {o0, o1, o2, o3};
+                if (hist) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < nvalid) atomicAdd(&myh[ov[j]], 1);
-        }
-        if (blurred) {
-            uint8_t *o = blurred + fo + (size_t)Y * W + X;
-            if (nvalid == 4 && b4)
-                *reinterpret_cast<uint32_t *>(o) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
-            else
-                for (int j = 0; j < nvalid; ++j) o[j] = (uint8_t)ov[j];
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nvalid) atomicAdd(&myh[ov[j]], 1);
+                }
+                if (blurred) {
+                    uint8_t *o = blurred + fo + (size_t)Y * W + Xo;
+                    if (FAST)
+                        *reinterpret_cast<uint32_t *>(o) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+                    else
+                        for (int j = 0; j < nvalid; ++j) o[j] = (uint8_t)ov[j];
+                }
+            }
         }
     }
     if (hist) {
@@ -967,10 +969,18 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
                   uint8_t *gray, uint8_t *blurred, int32_t *hist)
 {
     if (hist) CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * (size_t)n, h->stream));
-    dim3 grid((W + 127) / 128, (H + 31) / 32, n);
+    dim3 grid((W + 119) / 120, (H + 35) / 36, n);
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(enhanced) |
+                           reinterpret_cast<uintptr_t>(gray) | reinterpret_cast<uintptr_t>(blurred);
+    const bool fast = (W % 4 == 0) && (bits & 3) == 0;
     PROF(h, "k_finish");
-    if (minmax) k_finish<true><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
-    else k_finish<false><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);
+    if (minmax) {
+        if (fast) k_finish<true, true><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
+        else k_finish<true, false><<<grid, 256, 0, h->stream>>>(src, H, W, minmax, enhanced, gray, blurred, hist);
+    } else {
+        if (fast) k_finish<false, true><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);
+        else k_finish<false, false><<<grid, 256, 0, h->stream>>>(src, H, W, nullptr, enhanced, gray, blurred, hist);
+    }
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
