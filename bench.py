@@ -225,6 +225,7 @@ def main():
                           "piece_detector statistics + change_detector detect/update)" % args.frames,
               "frames_per_gpu": args.frames, "height": H, "width": W, "frame_kind": args.kind,
               "unique_frames": UNIQUE, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+              "numa": "each rank pinned to its GPU's CPUs (NVML affinity) before allocating page-locked buffers",
               "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU vs 126 MB)" % (args.frames * H * W * 3 / 1e6)}
 
     # ------------------------------------------------------------------ reference arm
@@ -278,6 +279,8 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from chessboard_vision_b200.sharding import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0
     from chessboard_vision_b200.engine import (Engine, grid_rects, _rect_array, STATS_DTYPE, SQ_PD_STATS, SQ_PD_SET_REF,
                                                SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
     eng = Engine(local_rank)

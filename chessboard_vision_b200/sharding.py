@@ -44,3 +44,24 @@ def gather_records(local, dst=0):
     parts = [np.frombuffer(b, dtype=np.dtype([tuple(d) if isinstance(d, list) else d for d in descr])).reshape(shape)
              for descr, shape, b in bucket]
     return np.concatenate(parts, axis=0)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that page-locked staging
+    buffers are allocated on the GPU's own NUMA node (matters when 8 ranks stream frames at once).
+    Returns the number of CPUs in the new affinity mask, or 0 when nothing was changed."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
