@@ -15,9 +15,17 @@ class CvbError(RuntimeError):
     pass
 
 
+class ColorProfile(C.Structure):
+    _fields_ = [("contrast", C.c_double), ("brightness", C.c_double),
+                ("hue_shift", C.c_float), ("sat_scale", C.c_float), ("val_scale", C.c_float),
+                ("radical_mode", C.c_int), ("target_hue", C.c_float), ("hue_window", C.c_float),
+                ("simd_block", C.c_int)]
+
+
 class EnhanceParams(C.Structure):
     _fields_ = [("clahe_clip_limit", C.c_double), ("tiles_x", C.c_int), ("tiles_y", C.c_int),
-                ("bilateral_d", C.c_int), ("sigma_color", C.c_double), ("sigma_space", C.c_double)]
+                ("bilateral_d", C.c_int), ("sigma_color", C.c_double), ("sigma_space", C.c_double),
+                ("use_color_profile", C.c_int), ("profile", ColorProfile)]
 
 
 class Rect(C.Structure):
@@ -79,6 +87,8 @@ SYMBOLS = [
     ("cvb_get_tables", _I, [_P, _P, _P, _P, _P]),
     ("cvb_get_bilateral_tables", _I, [_D, _D, _P, _P]),
     ("cvb_gaussian_kernel_q8", _I, [_I, _P]),
+    ("cvb_color_profile_default", None, [C.POINTER(ColorProfile)]),
+    ("cvb_color_profile_dev", _I, [_P, _P, _I, _I, _I, C.POINTER(ColorProfile), _P]),
     ("cvb_bgr2lab_dev", _I, [_P, _P, _I, _I, _I, _P]),
     ("cvb_lab2bgr_dev", _I, [_P, _P, _I, _I, _I, _P]),
     ("cvb_clahe_dev", _I, [_P, _P, _I, _I, _I, _D, _I, _I, _P, _P, _P]),

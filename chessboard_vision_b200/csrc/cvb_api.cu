@@ -8,6 +8,7 @@
 #include <cstring>
 #include <algorithm>
 
+static_assert(sizeof(cvb_color_profile) == 48 && sizeof(cvb_enhance_params) == 96, "ABI struct layout (see _lib.py)");
 static thread_local char g_err[512] = "";
 
 void cvb_set_error(const char *fmt, ...)
@@ -110,7 +111,7 @@ void cvb_destroy(cvb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
+    DevBuf *bufs[] = {&h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
                       &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks};
     for (DevBuf *b : bufs)
@@ -246,10 +247,20 @@ int cvb_event_elapsed_ms(void *start, void *stop, float *ms)
     return CVB_OK;
 }
 
+void cvb_color_profile_default(cvb_color_profile *p)
+{
+    // the defaults of frame_enhancer.py:61-68
+    p->contrast = 1.0; p->brightness = 0.0;
+    p->hue_shift = 0.f; p->sat_scale = 1.f; p->val_scale = 1.f;
+    p->radical_mode = 0; p->target_hue = 0.f; p->hue_window = 20.f;
+    p->simd_block = 32;
+}
 void cvb_enhance_params_default(cvb_enhance_params *p)
 {
     p->clahe_clip_limit = 3.0; p->tiles_x = 8; p->tiles_y = 8;
     p->bilateral_d = 9; p->sigma_color = 75.0; p->sigma_space = 75.0;
+    p->use_color_profile = 0;
+    cvb_color_profile_default(&p->profile);
 }
 void cvb_square_params_default(cvb_square_params *p)
 {
@@ -299,6 +310,13 @@ int cvb_get_perspective_transform(const float *src_xy4, const float *dst_xy4, do
 }
 
 // ---- stage-isolated entry points ----------------------------------------------------------
+int cvb_color_profile_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_color_profile *p, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && out && p, "null pointer");
+    CVB_REQUIRE(p->simd_block >= 0, "simd_block must be >= 0");
+    return launch_color_profile(h, bgr, n, H, W, *p, out);
+}
 int cvb_bgr2lab_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *lab)
 {
     REQ_H(h); REQ_IMG(n, H, W);
@@ -433,6 +451,12 @@ int cvb_enhance_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, cons
     const size_t fb = (size_t)H * W * 3;
     WS(ws_minmax, int32_t, 2 * n, minmax);
     WS(ws_sharp, uint8_t, fb * n, sharp);
+    if (p->use_color_profile) {
+        // step 0 of process_pipeline (frame_enhancer.py:167): one more pointwise pass, only when a profile is loaded
+        WS(ws_prof, uint8_t, fb * n, prof);
+        CVB_TRY(launch_color_profile(h, bgr, n, H, W, p->profile, prof));
+        bgr = prof;
+    }
     int32_t *hist = nullptr;
     uint8_t *lut = nullptr;
     // pass 1: tile histograms (+ min/max reset), LUTs

@@ -42,6 +42,84 @@ int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g
 }
 
 // ---------------------------------------------------------------------------------------
+// S0: apply_color_profile (frame_enhancer.py:56-99), pointwise.
+//   convertScaleAbs : |fma(v, alpha, beta)| rounded, saturated          (convert_scale.simd.hpp)
+//   BGR2HSV (8-bit) : integer, sdiv / hdiv tables, 12 fractional bits   (color_hsv RGB2HSV_b)
+//   NumPy step      : f32: radical-mode saturation, (h + shift) mod 180, scales, clip, truncate to u8
+//   HSV2BGR (8-bit) : f32 sectors with 1 - s*h formed by fnma; the 32-pixel vector body of a row
+//                     truncates, the row tail rounds to nearest even (measured against cv2 4.13)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_color_profile(const uint8_t *__restrict__ src, int H, int W, cvb_color_profile c,
+                                                       uint8_t *__restrict__ dst)
+{
+    __shared__ int s_sdiv[256], s_hdiv[256];
+    {
+        const int i = threadIdx.x;
+        // saturate_cast<int>((255 << 12) / (1. * i)), ((180 << 12) / (6. * i)): f64 quotient rounded to nearest even
+        s_sdiv[i] = i ? __double2int_rn(__ddiv_rn((double)(255 << 12), (double)i)) : 0;
+        s_hdiv[i] = i ? __double2int_rn(__ddiv_rn((double)(180 << 12), __dmul_rn(6.0, (double)i))) : 0;
+    }
+    __syncthreads();
+    const float a = (float)c.contrast, b = (float)c.brightness;
+    const int frame = blockIdx.z;
+    const int nvec = c.simd_block > 0 ? (W / c.simd_block) * c.simd_block : 0;
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const size_t o = ((size_t)frame * H * W + (size_t)y * W + x) * 3;
+    int ch[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ch[k] = round_u8(fabsf(__fmaf_rn((float)src[o + k], a, b)));
+    // BGR -> HSV
+    const int B = ch[0], G = ch[1], R = ch[2];
+    const int v = max(B, max(G, R)), vmin = min(B, min(G, R)), diff = v - vmin;
+    const int sat = (diff * s_sdiv[v] + (1 << 11)) >> 12;
+    int hue = v == R ? G - B : (v == G ? B - R + 2 * diff : R - G + 4 * diff);
+    hue = (hue * s_hdiv[diff] + (1 << 11)) >> 12;
+    if (hue < 0) hue += 180;
+    // NumPy f32 step
+    float hf = (float)clamp_u8(hue), sf = (float)sat, vf = (float)v;
+    if (c.radical_mode) {
+        float hd = fabsf(__fsub_rn(hf, c.target_hue));
+        hd = fminf(hd, __fsub_rn(180.f, hd));
+        sf = hd < c.hue_window ? __fmul_rn(sf, 2.0f) : __fmul_rn(sf, 0.5f);
+    }
+    float m = fmodf(__fadd_rn(hf, c.hue_shift), 180.f);      // np.remainder: fmod, then shifted into [0, 180)
+    if (m != 0.f) { if (m < 0.f) m = __fadd_rn(m, 180.f); } else m = 0.f;
+    hf = fminf(fmaxf(m, 0.f), 179.f);
+    sf = fminf(fmaxf(__fmul_rn(sf, c.sat_scale), 0.f), 255.f);
+    vf = fminf(fmaxf(__fmul_rn(vf, c.val_scale), 0.f), 255.f);
+    const int h8 = (int)hf, s8 = (int)sf, v8 = (int)vf;      // astype(np.uint8) truncates
+    // HSV -> BGR
+    const float s1 = __fmul_rn((float)s8, 1.f / 255.f), v1 = __fmul_rn((float)v8, 1.f / 255.f);
+    float hh = __fmul_rn((float)h8, 6.f / 180.f);
+    const float fl = floorf(hh);
+    int sector = (int)fl % 6;
+    hh = __fsub_rn(hh, fl);
+    float tab[4];
+    tab[0] = v1;
+    tab[1] = __fmul_rn(v1, __fsub_rn(1.f, s1));
+    tab[2] = __fmul_rn(v1, __fmaf_rn(-s1, hh, 1.f));
+    tab[3] = __fmul_rn(v1, __fmaf_rn(-s1, __fsub_rn(1.f, hh), 1.f));
+    // sector_data of HSV2RGB_native: {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} packed two bits per entry
+    const unsigned sel = sector == 0 ? 0x0Du : sector == 1 ? 0x21u : sector == 2 ? 0x13u : sector == 3 ? 0x18u
+                       : sector == 4 ? 0x34u : 0x06u;       // bits: b | g << 2 | r << 4
+    const bool vec = x < nvec;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float t = __fmul_rn(tab[(sel >> (2 * k)) & 3], 255.f);
+        dst[o + k] = (uint8_t)clamp_u8(vec ? (int)t : __float2int_rn(t));
+    }
+}
+int launch_color_profile(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_color_profile &p, uint8_t *out)
+{
+    dim3 grid((W + 63) / 64, (H + 3) / 4, n);
+    PROF(h, "k_color_profile");
+    k_color_profile<<<grid, 256, 0, h->stream>>>(bgr, H, W, p, out);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Pointwise colour conversions (stage-isolated API; the hot path uses k_fused)
 // ---------------------------------------------------------------------------------------
 template <bool FWD>

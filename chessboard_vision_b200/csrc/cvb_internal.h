@@ -64,7 +64,7 @@ struct cvb_handle {
     float *d_color = nullptr;
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
-    DevBuf ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
+    DevBuf ws_prof, ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
     DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
     cudaStream_t copy_stream = nullptr;
@@ -105,6 +105,7 @@ struct ClaheGeom {
 };
 int cvb_clahe_geom(int H, int W, double clip_limit, int tx, int ty, ClaheGeom *g);
 
+int launch_color_profile(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_color_profile &p, uint8_t *out);
 int launch_bgr2lab(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *lab);
 int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr);
 // histogram of L (from_bgr=1: src is BGR, L computed on the fly) or of a u8 plane

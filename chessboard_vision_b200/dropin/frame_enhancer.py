@@ -52,7 +52,7 @@ class ImageEnhancerB200:
         self.profile = self.load_profile()
 
     def _params(self):
-        return self._e.enhance_params(self.clahe.getClipLimit(), self.clahe.getTilesGridSize())
+        return self._e.enhance_params(self.clahe.getClipLimit(), self.clahe.getTilesGridSize(), profile=self.profile)
 
     @staticmethod
     def _frame(frame):
@@ -73,18 +73,11 @@ class ImageEnhancerB200:
         return {}
 
     def apply_color_profile(self, frame):
-        """frame_enhancer.py:56-99.  With no profile (the configuration of the hot path) this is the
-        identity.  A non-empty profile is the 'next' scope row: it is run by
-        the reference's own host code when that is importable, never approximated here."""
+        """frame_enhancer.py:56-99: contrast/brightness, HSV hue / saturation / value adjustment (one pointwise
+        kernel).  With no profile loaded (the configuration of the hot path) this is the identity."""
         if not self.profile:
             return frame
-        ref = load_reference_module("frame_enhancer")
-        if ref is None:
-            raise NotImplementedError("apply_color_profile with a non-empty color_profile.json is outside the "
-                                      "B200 hot path and the reference's frame_enhancer.py was not found on sys.path")
-        helper = ref.ImageEnhancerPython.__new__(ref.ImageEnhancerPython)
-        helper.profile = self.profile
-        return ref.ImageEnhancerPython.apply_color_profile(helper, frame)
+        return self._e.apply_color_profile(self._frame(frame), self.profile)
 
     def correct_lighting(self, frame):
         """frame_enhancer.py:101-120: BGR->LAB, CLAHE on L, LAB->BGR (fused kernel)."""
@@ -109,12 +102,10 @@ class ImageEnhancerB200:
 
     def process_pipeline(self, frame):
         """frame_enhancer.py:161-181: one call, four passes over the frame."""
-        frame = self.apply_color_profile(frame)
-        return self._e.process_pipeline(self._frame(frame), self._params())
+        return self._e.process_pipeline(self._frame(frame), self._params())     # step 0 runs inside when a profile is set
 
     # not in the reference: both results of the demo loop (frame_enhancer.py:218-219) in one launch sequence
     def process_and_analyze(self, frame):
-        frame = self.apply_color_profile(frame)
         enhanced, gray, binary, _ = self._e.enhance(self._frame(frame), self._params())
         return enhanced, gray, binary
 

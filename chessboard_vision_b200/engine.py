@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (EnhanceParams, PipelineParams, Rect, SquareParams, SquareStats, check,
+from ._lib import (ColorProfile, EnhanceParams, PipelineParams, Rect, SquareParams, SquareStats, check,
                    SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
 
 STATS_DTYPE = np.dtype([("n", "<i4"), ("has_ref", "<i4"), ("sum", "<u4"), ("sad", "<u4"), ("sumsq", "<u8"),
@@ -241,11 +241,33 @@ class Engine:
         return ms.value
 
     # -- parameters ----------------------------------------------------------------
-    def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0):
+    def color_profile_params(self, profile, simd_block=32):
+        """dict with the keys of color_profile.json -> cvb_color_profile.  NumPy applies the python scalars to
+        float32 arrays as float32 (frame_enhancer.py:79-89), hence the f32 fields."""
+        p = ColorProfile()
+        self.lib.cvb_color_profile_default(C.byref(p))
+        p.contrast = float(profile.get("contrast", 1.0)); p.brightness = float(profile.get("brightness", 0))
+        p.hue_shift = np.float32(profile.get("hue_shift", 0)); p.sat_scale = np.float32(profile.get("sat_scale", 1.0))
+        p.val_scale = np.float32(profile.get("val_scale", 1.0))
+        p.radical_mode = int(bool(profile.get("radical_mode", 0)))
+        p.target_hue = np.float32(profile.get("target_hue", 0)); p.hue_window = np.float32(profile.get("hue_window", 20))
+        p.simd_block = int(simd_block)
+        return p
+
+    def apply_color_profile(self, img, profile, simd_block=32):
+        """ImageEnhancer.apply_color_profile (frame_enhancer.py:56-99); identity for an empty profile."""
+        if not profile:
+            return img
+        return self._stage_p(self.lib.cvb_color_profile_dev, img, self.color_profile_params(profile, simd_block))
+
+    def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0, profile=None):
         p = EnhanceParams()
         self.lib.cvb_enhance_params_default(C.byref(p))
         p.clahe_clip_limit = float(clip); p.tiles_x, p.tiles_y = int(tiles[0]), int(tiles[1])
         p.bilateral_d = int(d); p.sigma_color = float(sigma_color); p.sigma_space = float(sigma_space)
+        if profile:
+            p.use_color_profile = 1
+            p.profile = self.color_profile_params(profile)
         return p
 
     # -- simple 1-in 1-out stages -----------------------------------------------------

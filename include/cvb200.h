@@ -83,12 +83,27 @@ int cvb_event_record(cvb_handle *h, void *ev);
 int cvb_event_elapsed_ms(void *start, void *stop, float *ms);   /* syncs on stop */
 
 /* ---- parameters -------------------------------------------------------------- */
+/* S0 colour profile (frame_enhancer.py:56-99, the values of color_profile.json).  NumPy applies the python
+ * scalars as f32, hence the float fields.  simd_block: pixels per vector block of OpenCV's HSV2BGR on the
+ * reference host (32 for the AVX2 build of opencv-python 4.13): the vector body truncates, the row tail
+ * rounds, and being bit-exact means reproducing that.                                                      */
+typedef struct {
+    double contrast, brightness;          /* cv2.convertScaleAbs(alpha, beta)    frame_enhancer.py:71 */
+    float  hue_shift, sat_scale, val_scale;   /*                                  frame_enhancer.py:87-89 */
+    int    radical_mode;                  /*                                      frame_enhancer.py:77-84 */
+    float  target_hue, hue_window;
+    int    simd_block;
+} cvb_color_profile;
+void cvb_color_profile_default(cvb_color_profile *p);
+
 typedef struct {
     double clahe_clip_limit;   /* frame_enhancer.py:28  default 3.0            */
     int    tiles_x, tiles_y;   /* tileGridSize           default 8,8 (<=16)    */
     int    bilateral_d;        /* frame_enhancer.py:131  must be 9             */
     double sigma_color;        /*                         75                    */
     double sigma_space;        /*                         75                    */
+    int    use_color_profile;  /* 0: step 0 of process_pipeline is the identity (no color_profile.json) */
+    cvb_color_profile profile; /* frame_enhancer.py:167                          */
 } cvb_enhance_params;
 void cvb_enhance_params_default(cvb_enhance_params *p);
 
@@ -101,6 +116,10 @@ int cvb_get_bilateral_tables(double sigma_color, double sigma_space,
 int cvb_gaussian_kernel_q8(int ksize, int *q /* ksize entries */);
 
 /* ---- frame_enhancer stages (stage-isolated entry points) -------------------- */
+/* S0 apply_color_profile: convertScaleAbs -> BGR2HSV -> f32 hue/sat/val maths -> HSV2BGR
+ *                                                frame_enhancer.py:56-99 */
+int cvb_color_profile_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                          const cvb_color_profile *p, uint8_t *out);
 /* S1 cv2.cvtColor(BGR2LAB)                       frame_enhancer.py:108 */
 int cvb_bgr2lab_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *lab);
 /* S3 cv2.cvtColor(LAB2BGR)                       frame_enhancer.py:120 */

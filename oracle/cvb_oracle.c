@@ -738,3 +738,120 @@ ORC_API void orc_cd_detect(const u8 *g, long n, const float *mean, const float *
     }
     *changed = cnt; *zmax = zm;
 }
+
+/* ------------------------------------------------------------------------ */
+/* S0  colour profile          frame_enhancer.py:56-99  ("next" scope row)   */
+/* OpenCV: convert_scale.simd.hpp cvtabs (f32 fma, |.|, round), color_hsv   */
+/* RGB2HSV_b (integer, hdiv/sdiv tables), HSV2RGB_b (f32 with fnma for the   */
+/* two hue-dependent terms; the 32-pixel vector body truncates, the scalar  */
+/* row tail rounds -- measured against cv2 4.13 on all 180*256*256 inputs);  */
+/* NumPy f32 arithmetic in between.                                          */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    double contrast, brightness;      /* convertScaleAbs alpha / beta          */
+    float hue_shift, sat_scale, val_scale;
+    int radical_mode;
+    float target_hue, hue_window;
+    int simd_block;                    /* pixels per vector block of HSV2BGR (32 on AVX2 builds); 0 = all scalar */
+} orc_color_profile;
+
+static int g_hsv_ready = 0;
+static int32_t g_sdiv[256], g_hdiv[256];
+static void hsv_tables_init(void)
+{
+    if (g_hsv_ready) return;
+    g_sdiv[0] = g_hdiv[0] = 0;
+    for (int i = 1; i < 256; i++) {
+        g_sdiv[i] = (int32_t)rint((255 << 12) / (1. * i));
+        g_hdiv[i] = (int32_t)rint((180 << 12) / (6. * i));
+    }
+    g_hsv_ready = 1;
+}
+ORC_API void orc_convert_scale_abs(const u8 *src, long n, double alpha, double beta, u8 *dst)
+{
+    const float a = (float)alpha, b = (float)beta;
+    for (long i = 0; i < n; i++) dst[i] = (u8)sat_u8((int)rintf(fabsf(fmaf((float)src[i], a, b))));
+}
+static inline void bgr2hsv_px(const u8 *p, u8 *o)
+{
+    int b = p[0], g = p[1], r = p[2];
+    int v = b > g ? b : g; if (r > v) v = r;
+    int vmin = b < g ? b : g; if (r < vmin) vmin = r;
+    int diff = v - vmin;
+    int s = (diff * g_sdiv[v] + (1 << 11)) >> 12;
+    int h = v == r ? g - b : (v == g ? b - r + 2 * diff : r - g + 4 * diff);
+    h = (h * g_hdiv[diff] + (1 << 11)) >> 12;
+    if (h < 0) h += 180;
+    o[0] = (u8)sat_u8(h); o[1] = (u8)s; o[2] = (u8)v;
+}
+ORC_API void orc_bgr2hsv(const u8 *bgr, long n_px, u8 *hsv)
+{
+    hsv_tables_init();
+    for (long i = 0; i < n_px; i++) bgr2hsv_px(bgr + 3 * i, hsv + 3 * i);
+}
+static inline void hsv2bgr_px(const u8 *p, u8 *o, int vector_body)
+{
+    static const int sector_data[6][3] = {{1, 3, 0}, {1, 0, 2}, {3, 0, 1}, {0, 2, 1}, {0, 1, 3}, {2, 1, 0}};
+    float h = (float)p[0], s = (float)p[1] * (1.f / 255.f), v = (float)p[2] * (1.f / 255.f);
+    float tab[4];
+    h = h * (6.f / 180.f);
+    float fl = floorf(h);
+    int sector = (int)fl;
+    h = h - fl;
+    sector %= 6; if (sector < 0) sector += 6;
+    tab[0] = v;
+    { float t = 1.f - s; tab[1] = v * t; }
+    /* both the vector body and the (compiler-contracted) scalar tail of the AVX2 build form 1 - s*h with one rounding */
+    tab[2] = v * fmaf(-s, h, 1.f);
+    { float omh = 1.f - h; tab[3] = v * fmaf(-s, omh, 1.f); }
+    for (int c = 0; c < 3; c++) {
+        float x = tab[sector_data[sector][c]] * 255.f;
+        /* the vector body truncates (v_trunc), the scalar tail rounds (saturate_cast -> cvRound) */
+        int q = vector_body ? (int)x : (int)rintf(x);
+        o[c] = (u8)sat_u8(q);
+    }
+}
+/* row-wise: the first (W / block) * block pixels of a row take the vector formula */
+ORC_API void orc_hsv2bgr(const u8 *hsv, int H, int W, int simd_block, u8 *bgr)
+{
+    const int nvec = simd_block > 0 ? (W / simd_block) * simd_block : 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            hsv2bgr_px(hsv + ((long)y * W + x) * 3, bgr + ((long)y * W + x) * 3, x < nvec);
+}
+/* NumPy part of apply_color_profile (frame_enhancer.py:75-97) on one pixel, f32 throughout */
+static inline void hsv_adjust_px(const u8 *p, const orc_color_profile *c, u8 *o)
+{
+    float h = (float)p[0], s = (float)p[1], v = (float)p[2];
+    if (c->radical_mode) {
+        float hd = fabsf(h - c->target_hue);
+        float alt = 180.f - hd;
+        if (alt < hd) hd = alt;
+        s = hd < c->hue_window ? s * 2.0f : s * 0.5f;
+    }
+    float hs = h + c->hue_shift;
+    float m = fmodf(hs, 180.f);
+    if (m != 0.f) { if (m < 0.f) m += 180.f; } else m = 0.f;
+    h = m;
+    s = s * c->sat_scale;
+    v = v * c->val_scale;
+    if (h < 0.f) h = 0.f; if (h > 179.f) h = 179.f;
+    if (s < 0.f) s = 0.f; if (s > 255.f) s = 255.f;
+    if (v < 0.f) v = 0.f; if (v > 255.f) v = 255.f;
+    o[0] = (u8)(int)h; o[1] = (u8)(int)s; o[2] = (u8)(int)v;
+}
+ORC_API void orc_apply_color_profile(const u8 *bgr, int H, int W, const orc_color_profile *c, u8 *out)
+{
+    hsv_tables_init();
+    const float a = (float)c->contrast, b = (float)c->brightness;
+    const int nvec = c->simd_block > 0 ? (W / c->simd_block) * c->simd_block : 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const u8 *p = bgr + ((long)y * W + x) * 3;
+            u8 t[3], hsv[3], adj[3];
+            for (int k = 0; k < 3; k++) t[k] = (u8)sat_u8((int)rintf(fabsf(fmaf((float)p[k], a, b))));
+            bgr2hsv_px(t, hsv);
+            hsv_adjust_px(hsv, c, adj);
+            hsv2bgr_px(adj, out + ((long)y * W + x) * 3, x < nvec);
+        }
+}

@@ -278,3 +278,49 @@ def cd_detect(g, mean, var, z_threshold=2.5):
     lib().orc_cd_detect(_p(g), C.c_long(g.size), _p(mean), _p(var), C.c_float(np.float32(z_threshold)),
                         C.byref(cnt), C.byref(zmax))
     return cnt.value, zmax.value
+
+
+# --- S0 colour profile ("next" scope row) ----------------------------------------------
+class ColorProfile(C.Structure):
+    _fields_ = [("contrast", C.c_double), ("brightness", C.c_double),
+                ("hue_shift", C.c_float), ("sat_scale", C.c_float), ("val_scale", C.c_float),
+                ("radical_mode", C.c_int), ("target_hue", C.c_float), ("hue_window", C.c_float),
+                ("simd_block", C.c_int)]
+
+
+def color_profile_struct(profile, simd_block=32):
+    """frame_enhancer.py:61-68 defaults; NumPy turns the python scalars into f32 (weak scalars)."""
+    p = ColorProfile()
+    p.contrast = float(profile.get("contrast", 1.0)); p.brightness = float(profile.get("brightness", 0))
+    p.hue_shift = np.float32(profile.get("hue_shift", 0)); p.sat_scale = np.float32(profile.get("sat_scale", 1.0))
+    p.val_scale = np.float32(profile.get("val_scale", 1.0)); p.radical_mode = int(bool(profile.get("radical_mode", 0)))
+    p.target_hue = np.float32(profile.get("target_hue", 0)); p.hue_window = np.float32(profile.get("hue_window", 20))
+    p.simd_block = int(simd_block)
+    return p
+
+
+def convert_scale_abs(img, alpha, beta):
+    img = _u8(img); out = np.empty_like(img)
+    lib().orc_convert_scale_abs(_p(img), C.c_long(img.size), C.c_double(alpha), C.c_double(beta), _p(out))
+    return out
+
+
+def bgr2hsv(bgr):
+    bgr = _u8(bgr); out = np.empty_like(bgr)
+    lib().orc_bgr2hsv(_p(bgr), C.c_long(bgr.size // 3), _p(out))
+    return out
+
+
+def hsv2bgr(hsv, simd_block=32):
+    hsv = _u8(hsv); H, W, _ = hsv.shape; out = np.empty_like(hsv)
+    lib().orc_hsv2bgr(_p(hsv), C.c_int(H), C.c_int(W), C.c_int(simd_block), _p(out))
+    return out
+
+
+def apply_color_profile(bgr, profile, simd_block=32):
+    if not profile:
+        return bgr
+    bgr = _u8(bgr); H, W, _ = bgr.shape; out = np.empty_like(bgr)
+    p = color_profile_struct(profile, simd_block)
+    lib().orc_apply_color_profile(_p(bgr), C.c_int(H), C.c_int(W), C.byref(p), _p(out))
+    return out

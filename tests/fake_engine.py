@@ -34,8 +34,11 @@ class FakeEngine:
     h = 1
     launches = 0
 
-    def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0):
-        return dict(clip=clip, tiles=tiles)
+    def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0, profile=None):
+        return dict(clip=clip, tiles=tiles, profile=profile)
+
+    def apply_color_profile(self, img, profile, simd_block=32):
+        return O.apply_color_profile(img, profile, simd_block)
 
     def clahe(self, plane, clip=3.0, tiles=(8, 8), return_tables=False):
         return O.clahe(plane, clip, tiles, return_tables)
@@ -62,10 +65,12 @@ class FakeEngine:
         return O.prepare_analysis(img)
 
     def process_pipeline(self, img, params=None):
+        if params and params.get("profile"):
+            img = O.apply_color_profile(img, params["profile"])
         return O.process_pipeline(img, True)
 
     def enhance(self, img, params=None):
-        enh = O.process_pipeline(img, True)
+        enh = self.process_pipeline(img, params)
         g, b, t, _ = O.prepare_analysis(enh, True)
         return enh, g, b, t
 

@@ -33,7 +33,8 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_sizes_match_header():
     assert C.sizeof(_lib.SquareStats) == 128
     assert C.sizeof(_lib.Rect) == 16
-    assert C.sizeof(_lib.EnhanceParams) == 40
+    assert C.sizeof(_lib.ColorProfile) == 48
+    assert C.sizeof(_lib.EnhanceParams) == 96
     assert C.sizeof(_lib.SquareParams) == 32
 
 

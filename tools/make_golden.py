@@ -176,6 +176,25 @@ def main():
     cd_out["top40rows_1_1"] = {"pct_changed": d4[(1, 1)]["pct_changed"], "intensity": d4[(1, 1)]["intensity"]}
     json.dump(cd_out, open(os.path.join(OUT, "change_detector.json"), "w"), indent=1)
 
+    # ---- 7. colour profile (step 0 of process_pipeline; "next" scope row) ----------------------------
+    profiles = {"repo": json.load(open(os.path.join(REF, "color_profile.json"))),
+                "radical": {"hue_shift": 12, "sat_scale": 1.2, "val_scale": 0.9, "contrast": 1.1, "brightness": 5,
+                            "radical_mode": 1, "target_hue": 30, "hue_window": 26},
+                "fractional": {"hue_shift": 17.5, "sat_scale": 1.3, "val_scale": 0.8, "contrast": 0.9, "brightness": 12}}
+    cp = {"profiles": np.array(json.dumps(profiles))}
+    cp_kat = {}
+    for pname, prof in profiles.items():
+        e2 = fe.ImageEnhancer()
+        e2.profile = prof
+        for name, img in (("board_90x121", synth.board_frame(90, 121, 21)), ("noise_64x96", synth.noise_frame(64, 96, 22))):
+            cp[pname + "/" + name] = e2.apply_color_profile(img)
+        big = synth.noise_frame(1080, 1920, 0)
+        cp_kat[pname] = {"apply_1920x1080": sha(e2.apply_color_profile(big)),
+                         "process_pipeline_board_96x128": None}
+        cp[pname + "/pipeline_board_96x128"] = e2.process_pipeline(synth.board_frame(96, 128, 1))
+    cp["kat"] = np.array(json.dumps(cp_kat))
+    np.savez_compressed(os.path.join(OUT, "color_profile.npz"), **cp)
+
     # ---- 6. warp on a small frame (full output) ---------------------------------------------------
     img = synth.noise_frame(270, 480, 9)
     pts = synth.calib_points(270, 480)
