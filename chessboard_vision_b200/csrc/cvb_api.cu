@@ -61,8 +61,6 @@ static void prof_clear(cvb_handle *h)
     CVB_REQUIRE((n) >= 1 && (n) <= 65535 && (H) >= 1 && (W) >= 1 && (H) <= 32768 && (W) <= 32768,              \
                 "bad batch/shape n=%d H=%d W=%d", (n), (H), (W))
 
-static void drop_rect_cache(cvb_handle *h);
-
 extern "C" {
 
 int cvb_version(void) { return CVB_VERSION; }
@@ -125,7 +123,6 @@ void cvb_destroy(cvb_handle *h)
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
     }
     prof_clear(h);
-    drop_rect_cache(h);
     delete h;
 }
 
@@ -493,10 +490,9 @@ int cvb_enhance(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cv
 }
 
 // ---- warp ------------------------------------------------------------------------------------
-static std::map<cvb_handle *, std::vector<double>> g_mat_cache;
 static int upload_inverse_mats(cvb_handle *h, const double *M9, int n_mats, double **d_out)
 {
-    std::vector<double> &last = g_mat_cache[h];
+    std::vector<double> &last = h->mat_cache;
     if (h->ws_mats.p && last.size() == (size_t)n_mats * 9 && memcmp(last.data(), M9, sizeof(double) * 9 * n_mats) == 0) {
         *d_out = (double *)h->ws_mats.p;      // same matrices as the previous call: already resident
         return CVB_OK;
@@ -604,18 +600,6 @@ int cvb_state_reset(cvb_handle *h, cvb_state *s, int stream)
 }
 
 // rects/select -> device, masks per distinct shape (cached on the handle by content)
-struct RectCache {
-    std::vector<cvb_rect> rects;
-    std::vector<uint8_t> select;
-    bool has_select = false;
-    int max_px = 0;
-    size_t mask_bytes = 0;
-};
-static std::map<cvb_handle *, RectCache> g_rect_cache;
-} // extern "C" (paused: C++ linkage for the helper below)
-static void drop_rect_cache(cvb_handle *h) { g_rect_cache.erase(h); g_mat_cache.erase(h); }
-extern "C" {
-
 static int stage_rects(cvb_handle *h, const cvb_rect *rects, int n_sq, const uint8_t *select, int BH, int BW,
                        cvb_rect **d_rects, int32_t **d_ofs, uint8_t **d_masks, uint8_t **d_select, int *max_px)
 {
@@ -625,7 +609,7 @@ static int stage_rects(cvb_handle *h, const cvb_rect *rects, int n_sq, const uin
                         rects[i].x + rects[i].w <= BW && rects[i].y + rects[i].h <= BH,
                     "square %d (%d,%d %dx%d) outside the %dx%d board", i, rects[i].x, rects[i].y, rects[i].w,
                     rects[i].h, BW, BH);
-    RectCache &c = g_rect_cache[h];
+    RectCache &c = h->rect_cache;
     const bool same_rects = (int)c.rects.size() == n_sq && memcmp(c.rects.data(), rects, sizeof(cvb_rect) * n_sq) == 0 &&
                             h->ws_rects.p != nullptr;
     const bool same_sel = same_rects && c.has_select == (select != nullptr) &&

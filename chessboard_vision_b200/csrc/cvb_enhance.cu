@@ -671,10 +671,10 @@ static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
     auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // per device: one handle per GPU, possibly several GPUs in one process
+    if (!h->fused_attr_done.count((const void *)kern)) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
-        attr_done = true;
+        h->fused_attr_done.insert((const void *)kern);
     }
     dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, n);
     PROF(h, "k_fused");

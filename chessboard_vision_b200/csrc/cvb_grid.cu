@@ -386,8 +386,7 @@ int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, 
         kern = k_squares<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE>; break;
     default: break;
     }
-    static std::map<void *, size_t> attr_set;
-    size_t &cur = attr_set[(void *)kern];
+    size_t &cur = h->squares_smem_attr[(const void *)kern];     // per handle = per device
     if (smem > 48 * 1024 && smem > cur) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <set>
 #include "../../include/cvb200.h"
 
 // ---- error plumbing ---------------------------------------------------------
@@ -51,7 +52,20 @@ struct DevBuf {
 
 struct ProfRec { const char *name; cudaEvent_t e0, e1; };
 
+// staged copies of the host-side rectangle list / matrices of the last call (content-compared)
+struct RectCache {
+    std::vector<cvb_rect> rects;
+    std::vector<uint8_t> select;
+    bool has_select = false;
+    int max_px = 0;
+    size_t mask_bytes = 0;
+};
+
 struct cvb_handle {
+    RectCache rect_cache;
+    std::vector<double> mat_cache;
+    std::set<const void *> fused_attr_done;             // kernels whose dynamic-smem attribute is set on this device
+    std::map<const void *, size_t> squares_smem_attr;
     bool profiling = false;
     std::vector<ProfRec> prof;
     int device = 0;
