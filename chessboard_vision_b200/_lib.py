@@ -104,6 +104,8 @@ SYMBOLS = [
     ("cvb_enhance", _I, [_P, _P, _I, _I, _I, C.POINTER(EnhanceParams), _P, _P, _P, _P]),
     ("cvb_get_perspective_transform", _I, [_P, _P, _P]),
     ("cvb_warp_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
+    ("cvb_canny_dev", _I, [_P, _P, _I, _I, _I, _D, _D, _P]),
+    ("cvb_projections_dev", _I, [_P, _P, _I, _I, _I, _P, _P]),
     ("cvb_state_create", _I, [_P, _I, _I, _I, C.POINTER(_P)]),
     ("cvb_state_destroy", None, [_P]),
     ("cvb_square_params_default", None, [C.POINTER(SquareParams)]),

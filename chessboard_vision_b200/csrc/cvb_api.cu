@@ -523,6 +523,20 @@ int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const d
     return launch_warp(h, bgr, n, H, W, d_m, n_mats, out_h, out_w, warped);
 }
 
+int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh,
+                  uint8_t *edges)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(gray && edges, "null image pointer");
+    return launch_canny(h, gray, n, H, W, low_thresh, high_thresh, edges);
+}
+int cvb_projections_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, uint32_t *row_sums, uint32_t *col_sums)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(plane && row_sums && col_sums, "null pointer");
+    return launch_projections(h, plane, n, H, W, row_sums, col_sums);
+}
+
 // ---- per-square ---------------------------------------------------------------------------------
 int cvb_state_create(cvb_handle *h, int n_streams, int BH, int BW, cvb_state **out)
 {

@@ -145,6 +145,10 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
 int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t);
 int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const int32_t *otsu_t, uint8_t *dst);
 
+// ---- cvb_canny.cu -------------------------------------------------------------------------
+int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh, uint8_t *edges);
+int launch_projections(cvb_handle *h, const uint8_t *plane, int n, int H, int W, uint32_t *rows, uint32_t *cols);
+
 // ---- cvb_grid.cu ----------------------------------------------------------------------
 int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats,
                 int out_h, int out_w, uint8_t *warped);

@@ -7,7 +7,6 @@ views (one common parent array) and hand the parent plus the rectangles to the
 batched square kernel without repacking.
 """
 from chessboard_vision_b200.engine import grid_rects
-from chessboard_vision_b200.hostapi import load_reference_module
 
 
 def _split(img_warped, rects, keys):
@@ -34,14 +33,13 @@ class SmartGridExtractor:
         self.debug = debug
 
     def refine_grid(self, img_warped):
-        """grid_extractor.py:66-121 (Canny + projection peaks): calibration-time code outside the hot
-        path; run by the reference's own implementation."""
-        ref = load_reference_module("grid_extractor")
-        if ref is None:
-            raise NotImplementedError("refine_grid is outside the B200 hot path and the reference's "
-                                      "grid_extractor.py was not found on sys.path")
-        helper = ref.SmartGridExtractor(debug=self.debug)
-        self.grid_lines_x, self.grid_lines_y = helper.refine_grid(img_warped)
+        """grid_extractor.py:66-121: Canny edges, row / column projections, window arg-max around the
+        seven expected inner lines (calibration time; SURVEY.md 8f rank 3, built in round 1)."""
+        from chessboard_vision_b200.engine import default_engine
+        self.grid_lines_x, self.grid_lines_y = default_engine().refine_grid(img_warped)
+        if self.debug:
+            print(f"Refined X: {self.grid_lines_x}")
+            print(f"Refined Y: {self.grid_lines_y}")
         return self.grid_lines_x, self.grid_lines_y
 
     def split_board(self, img_warped):

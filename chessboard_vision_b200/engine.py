@@ -416,6 +416,52 @@ class Engine:
         check(self.lib.cvb_warp_dev(self.h, src.ptr, n, H, W, M.ctypes.data, n_mats, int(oh), int(ow), dst.ptr))
         return self._out(dst, tmp, [src] if tmp else [])
 
+    # -- Canny / grid refinement (calibration time) ----------------------------------------------
+    def canny(self, gray, low=50, high=150):
+        return self._canny(gray, low, high)
+
+    def _canny(self, gray, low, high):
+        single, n, H, W = _as_batch(gray, 1)
+        src, tmp = self._in(gray)
+        dst = self.empty((H, W) if single else (n, H, W))
+        check(self.lib.cvb_canny_dev(self.h, src.ptr, n, H, W, float(low), float(high), dst.ptr))
+        return self._out(dst, tmp, [src] if tmp else [])
+
+    def projections(self, plane):
+        """-> (row_sums, col_sums) like np.sum(plane, axis=1), np.sum(plane, axis=0) (as uint64)."""
+        single, n, H, W = _as_batch(plane, 1)
+        src, tmp = self._in(plane)
+        rows, cols = self.empty((n, H), np.uint32), self.empty((n, W), np.uint32)
+        check(self.lib.cvb_projections_dev(self.h, src.ptr, n, H, W, rows.ptr, cols.ptr))
+        r, c = rows.get().astype(np.uint64), cols.get().astype(np.uint64)
+        rows.free(); cols.free()
+        if tmp:
+            src.free()
+        return (r[0], c[0]) if single else (r, c)
+
+    def refine_grid(self, img_warped):
+        """SmartGridExtractor.refine_grid (grid_extractor.py:66-121): gray -> Canny(50,150) -> edge projections on
+        the GPU, then the seven window arg-max positions per axis (nine numbers each) on the host."""
+        img = np.ascontiguousarray(img_warped, np.uint8)
+        h, w = img.shape[:2]
+        g = self.upload(img)
+        gray = self.gray(g)
+        edges = self._canny(gray, 50, 150)
+        row_proj, col_proj = self.projections(edges)
+        for t in (g, gray, edges):
+            t.free()
+
+        def lines(proj, length):
+            step = length / 8.0
+            out = [0]
+            for i in range(1, 8):
+                c, r = int(i * step), int(step * 0.3)
+                window = proj[max(0, c - r):min(length, c + r)]
+                out.append(max(0, c - r) + np.argmax(window) if len(window) > 0 else c)
+            out.append(length)
+            return out
+        return lines(col_proj, w), lines(row_proj, h)
+
     # -- squares ---------------------------------------------------------------------------------
     def square_params(self, ops=SQ_PD_STATS, pd_blur=5, cd_blur=5, z_threshold=2.5, alpha=0.1,
                       initial_variance=100.0, min_variance=10.0):

@@ -175,6 +175,14 @@ int cvb_get_perspective_transform(const float *src_xy4, const float *dst_xy4, do
 int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                  const double *M9, int n_mats, int out_h, int out_w, uint8_t *warped);
 
+/* ---- SmartGridExtractor.refine_grid building blocks (calibration time) -------- */
+/* cv2.Canny(gray, low, high) (aperture 3, L1 gradient)   grid_extractor.py:74 */
+int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W,
+                  double low_thresh, double high_thresh, uint8_t *edges);
+/* np.sum(plane, axis=1) / axis=0 as uint32 (DEVICE, n*H and n*W)  grid_extractor.py:78-80 */
+int cvb_projections_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
+                        uint32_t *row_sums, uint32_t *col_sums);
+
 /* ---- per-square statistics ------------------------------------------------------ */
 /* A "board" is an image (warped board or an atlas of packed squares) of
  * BH x BW x C (C = 1 or 3); squares are rectangles inside it

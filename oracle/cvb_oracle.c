@@ -855,3 +855,90 @@ ORC_API void orc_apply_color_profile(const u8 *bgr, int H, int W, const orc_colo
             hsv2bgr_px(adj, out + ((long)y * W + x) * 3, x < nvec);
         }
 }
+
+/* ------------------------------------------------------------------------ */
+/* Canny + grid refinement     grid_extractor.py:66-121 ("next" scope row)   */
+/* OpenCV imgproc/src/canny.cpp, 8-bit input, aperture 3, L1 magnitude:     */
+/* Sobel 3x3 with BORDER_REPLICATE, |dx|+|dy|, non-maximum suppression with */
+/* tan(22.5deg) in Q15 (13573), zeros outside the image, hysteresis = every  */
+/* candidate 8-connected to a candidate above the high threshold.           */
+/* ------------------------------------------------------------------------ */
+ORC_API void orc_canny(const u8 *src, int H, int W, double low_thresh, double high_thresh, u8 *dst)
+{
+    if (low_thresh > high_thresh) { double t = low_thresh; low_thresh = high_thresh; high_thresh = t; }
+    const int low = (int)floor(low_thresh), high = (int)floor(high_thresh);
+    const long n = (long)H * W;
+    int16_t *dx = (int16_t *)malloc(n * 2), *dy = (int16_t *)malloc(n * 2);
+    int32_t *mag = (int32_t *)calloc((long)(H + 2) * (W + 2), 4);
+    u8 *map = (u8 *)malloc(n);
+#define S(yy, xx) ((int)src[(long)((yy) < 0 ? 0 : (yy) >= H ? H - 1 : (yy)) * W + ((xx) < 0 ? 0 : (xx) >= W ? W - 1 : (xx))])
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int gx = (S(y - 1, x + 1) + 2 * S(y, x + 1) + S(y + 1, x + 1)) - (S(y - 1, x - 1) + 2 * S(y, x - 1) + S(y + 1, x - 1));
+            int gy = (S(y + 1, x - 1) + 2 * S(y + 1, x) + S(y + 1, x + 1)) - (S(y - 1, x - 1) + 2 * S(y - 1, x) + S(y - 1, x + 1));
+            dx[(long)y * W + x] = (int16_t)gx; dy[(long)y * W + x] = (int16_t)gy;
+            mag[(long)(y + 1) * (W + 2) + x + 1] = abs(gx) + abs(gy);
+        }
+#undef S
+    long *stack = (long *)malloc(n * sizeof(long)), sp = 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int32_t *mp = mag + (long)(y + 1) * (W + 2) + x + 1;
+            const int m = mp[0];
+            int cand = 0;
+            if (m > low) {
+                const int xs = dx[(long)y * W + x], ys = dy[(long)y * W + x];
+                const long ax = abs(xs), ay = (long)abs(ys) << 15;
+                const long tg22x = ax * 13573, tg67x = tg22x + (ax << 16);
+                if (ay < tg22x) cand = m > mp[-1] && m >= mp[1];
+                else if (ay > tg67x) cand = m > mp[-(W + 2)] && m >= mp[W + 2];
+                else { const int s = (xs ^ ys) < 0 ? -1 : 1; cand = m > mp[-(W + 2) - s] && m > mp[(W + 2) + s]; }
+            }
+            u8 v = 1;                      /* 1: not an edge, 0: weak candidate, 2: edge */
+            if (cand) { v = m > high ? 2 : 0; if (v == 2) stack[sp++] = (long)y * W + x; }
+            map[(long)y * W + x] = v;
+        }
+    while (sp) {
+        const long i = stack[--sp];
+        const int y = (int)(i / W), x = (int)(i % W);
+        for (int yy = y - 1; yy <= y + 1; yy++)
+            for (int xx = x - 1; xx <= x + 1; xx++)
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W && map[(long)yy * W + xx] == 0) {
+                    map[(long)yy * W + xx] = 2; stack[sp++] = (long)yy * W + xx;
+                }
+    }
+    for (long i = 0; i < n; i++) dst[i] = map[i] == 2 ? 255 : 0;
+    free(dx); free(dy); free(mag); free(map); free(stack);
+}
+
+/* find_internal_lines (grid_extractor.py:83-110): border 0, seven window arg-max positions, border `length` */
+static void internal_lines(const uint64_t *proj, int length, int32_t *lines)
+{
+    const double step = length / 8.0;
+    lines[0] = 0;
+    for (int i = 1; i < 8; i++) {
+        const int center = (int)(i * step), radius = (int)(step * 0.3);
+        int start = center - radius; if (start < 0) start = 0;
+        int end = center + radius; if (end > length) end = length;
+        if (end > start) {
+            int best = start;
+            for (int k = start + 1; k < end; k++) if (proj[k] > proj[best]) best = k;   /* np.argmax: first maximum */
+            lines[i] = best;
+        } else lines[i] = center;
+    }
+    lines[8] = length;
+}
+/* SmartGridExtractor.refine_grid: gray -> Canny(50,150) -> edge projections -> grid lines */
+ORC_API void orc_refine_grid(const u8 *bgr, int H, int W, int32_t *grid_x9, int32_t *grid_y9, u8 *edges_out)
+{
+    const long n = (long)H * W;
+    u8 *g = (u8 *)malloc(n), *e = edges_out ? edges_out : (u8 *)malloc(n);
+    orc_gray(bgr, H, W, 3L * W, g);
+    orc_canny(g, H, W, 50, 150, e);
+    uint64_t *rows = (uint64_t *)calloc(H, 8), *cols = (uint64_t *)calloc(W, 8);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) { rows[y] += e[(long)y * W + x]; cols[x] += e[(long)y * W + x]; }
+    internal_lines(cols, W, grid_x9);
+    internal_lines(rows, H, grid_y9);
+    free(g); if (!edges_out) free(e); free(rows); free(cols);
+}

@@ -324,3 +324,18 @@ def apply_color_profile(bgr, profile, simd_block=32):
     p = color_profile_struct(profile, simd_block)
     lib().orc_apply_color_profile(_p(bgr), C.c_int(H), C.c_int(W), C.byref(p), _p(out))
     return out
+
+
+# --- Canny / grid refinement ("next" scope row) ---------------------------------------------
+def canny(gray_u8, low=50, high=150):
+    g = _u8(gray_u8); H, W = g.shape; out = np.empty_like(g)
+    lib().orc_canny(_p(g), C.c_int(H), C.c_int(W), C.c_double(low), C.c_double(high), _p(out))
+    return out
+
+
+def refine_grid(bgr, return_edges=False):
+    """SmartGridExtractor.refine_grid (grid_extractor.py:66-121) -> (grid_x, grid_y) lists of 9 ints."""
+    bgr = _u8(bgr); H, W, _ = bgr.shape
+    gx = np.empty(9, np.int32); gy = np.empty(9, np.int32); e = np.empty((H, W), np.uint8)
+    lib().orc_refine_grid(_p(bgr), C.c_int(H), C.c_int(W), _p(gx), _p(gy), _p(e))
+    return (gx.tolist(), gy.tolist(), e) if return_edges else (gx.tolist(), gy.tolist())

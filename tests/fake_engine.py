@@ -74,6 +74,9 @@ class FakeEngine:
         g, b, t, _ = O.prepare_analysis(enh, True)
         return enh, g, b, t
 
+    def refine_grid(self, img):
+        return O.refine_grid(img)
+
     def get_perspective_transform(self, s, d):
         return O.get_perspective(s, d)
 

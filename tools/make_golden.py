@@ -195,6 +195,20 @@ def main():
     cp["kat"] = np.array(json.dumps(cp_kat))
     np.savez_compressed(os.path.join(OUT, "color_profile.npz"), **cp)
 
+    # ---- 8. Canny + refine_grid (calibration-time "next" scope row) -------------------------------
+    rg = {}
+    for seed in (7, 8, 9):
+        b0, b1 = synth.board_with_pieces(seed, seed, 620)
+        for tag, im in (("plain", b0), ("pieces", b1)):
+            sgx = ge.SmartGridExtractor()
+            gx, gy = sgx.refine_grid(im)
+            edges = cv2.Canny(cv2.cvtColor(im, cv2.COLOR_BGR2GRAY), 50, 150)
+            rg["%d_%s" % (seed, tag)] = {"grid_x": [int(v) for v in gx], "grid_y": [int(v) for v in gy],
+                                         "edges_sha": sha(edges), "edge_px": int(np.count_nonzero(edges))}
+    small = synth.board_frame(97, 133, 3)
+    rg["canny_97x133_30_100"] = sha(cv2.Canny(cv2.cvtColor(small, cv2.COLOR_BGR2GRAY), 30, 100))
+    json.dump(rg, open(os.path.join(OUT, "refine_grid.json"), "w"), indent=1)
+
     # ---- 6. warp on a small frame (full output) ---------------------------------------------------
     img = synth.noise_frame(270, 480, 9)
     pts = synth.calib_points(270, 480)
