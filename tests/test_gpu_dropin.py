@@ -136,3 +136,55 @@ def test_piece_detector_class(mods):
     # the references of squares that were processed and stable now hold the current frame
     res2, vis2 = pd.detect_all_pieces(sq_cur)
     assert vis2 <= vis
+
+
+def test_ragged_and_empty_square_dicts(mods, oracle):
+    """Squares of different sizes that are not views of one board (atlas path), empty dicts, a missing key."""
+    rng = np.random.default_rng(5)
+    shapes = {(c, r): (40 + 3 * r + c, 37 + 2 * c + r) for r in range(3) for c in range(4)}
+    ref = {k: rng.integers(0, 256, s + (3,), dtype=np.uint8) for k, s in shapes.items()}
+    cur = {k: (v if (k[0] + k[1]) % 3 else 255 - v) for k, v in ref.items()}
+    cd = mods["change_detector"].ChangeDetector()
+    assert cd.detect_changes_detailed({}) == {} and cd.detect_changes({}) == {}
+    cd.calibrate(ref)
+    det = cd.detect_changes_detailed(cur)
+    for k in ref:
+        g0 = oracle.square_preprocess(np.ascontiguousarray(ref[k]), 5)
+        g1 = oracle.square_preprocess(np.ascontiguousarray(cur[k]), 5)
+        m, v = oracle.cd_calibrate(g0, 100.0)
+        assert np.array_equal(cd.means[k], m)
+        cnt, zmax = oracle.cd_detect(g1, m, v, 2.5)
+        pct = cnt / g1.size * 100
+        if pct < 5.0:
+            assert k not in det
+        else:
+            assert det[k]["pct_changed"] == pct and det[k]["z_score"] == float(np.float32(zmax))
+    sub = {k: cur[k] for k in list(cur)[:5]}                 # a subset of the calibrated squares
+    assert set(cd.detect_changes_detailed(sub)) <= set(sub)
+    cd.update_all_references({})                              # nothing to update: no error
+    pd = mods["piece_detector"].PieceDetector()
+    assert pd.detect_all_pieces({}) == ({}, set())
+    pd.update_references(ref)
+    res, vis = pd.detect_all_pieces(cur)
+    want = {k for k in ref if float(np.mean(np.abs(oracle.square_preprocess(np.ascontiguousarray(cur[k]), 5).astype(int) -
+                                                      oracle.square_preprocess(np.ascontiguousarray(ref[k]), 5)))) > 25}
+    assert vis == want
+
+
+def test_error_paths(engine):
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        engine.bgr2lab(np.zeros((4, 4, 3), np.float32))                      # wrong dtype
+    with _pt.raises(ValueError):
+        engine.bgr2lab(np.zeros((4, 4), np.uint8))                           # wrong rank
+    with _pt.raises(ValueError):
+        engine.clahe(np.zeros((64, 64), np.uint8), 3.0, (32, 8))             # tile grid beyond 16
+    big = np.zeros((400, 400), np.uint8)
+    with _pt.raises(ValueError):
+        engine.squares(big, [(0, 0, 400, 400)], engine.square_params())      # square too large for shared memory
+    st = engine.new_state(1, 50, 50)
+    with _pt.raises(Exception):
+        engine.squares(np.zeros((60, 60), np.uint8), [(0, 0, 10, 10)], engine.square_params(), st)   # state / board mismatch
+    with _pt.raises(Exception):
+        engine.squares(np.zeros((50, 50), np.uint8), [(0, 0, 10, 10)], engine.square_params(), st, stream0=3)
+    st.free()
