@@ -56,6 +56,29 @@ class PipelineParams(C.Structure):
                 ("warp_enhanced", C.c_int), ("board_size", C.c_int)]
 
 
+HOUGH_MAX_CIRCLES, HOUGH_MAX_DIM = 16, 128
+HOUGH_OK, HOUGH_SKIPPED = 0, 1
+
+
+class HoughParams(C.Structure):
+    _fields_ = [("dp", C.c_float), ("min_dist", C.c_float), ("param1", C.c_double), ("param2", C.c_double),
+                ("min_radius_ratio", C.c_double), ("max_radius_ratio", C.c_double),
+                ("min_radius", C.c_int), ("max_radius", C.c_int), ("min_dist_div", C.c_int), ("reserved", C.c_int)]
+
+
+class HoughSquare(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("min_radius", C.c_int32), ("max_radius", C.c_int32), ("acc_rows", C.c_int32), ("acc_cols", C.c_int32),
+                ("n_bins", C.c_int32), ("min_dist", C.c_float)]
+
+
+class HoughResult(C.Structure):
+    _fields_ = [("count", C.c_int32), ("n_edges", C.c_int32), ("n_centers", C.c_int32), ("status", C.c_int32),
+                ("xyr", (C.c_float * 3) * HOUGH_MAX_CIRCLES), ("support", C.c_int32 * HOUGH_MAX_CIRCLES)]
+
+
+assert C.sizeof(HoughParams) == 56 and C.sizeof(HoughSquare) == 40 and C.sizeof(HoughResult) == 272
+
 SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE = 1, 2, 4, 8, 16
 PLANE_PD_REF, PLANE_CD_MEAN, PLANE_CD_VAR, PLANE_PD_CUR, PLANE_FLAGS = 0, 1, 2, 3, 4
 
@@ -113,6 +136,10 @@ SYMBOLS = [
     ("cvb_state_get", _I, [_P, _P, _I, _I, _P]),
     ("cvb_state_set", _I, [_P, _P, _I, _I, _P]),
     ("cvb_state_reset", _I, [_P, _P, _I]),
+    ("cvb_hough_params_default", None, [C.POINTER(HoughParams)]),
+    ("cvb_hough_geometry", _I, [_P, _I, C.POINTER(HoughParams), _P]),
+    ("cvb_hough_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _P, C.POINTER(HoughParams), _P]),
+    ("cvb_hough_state", _I, [_P, _P, _I, _I, _P, _I, _P, C.POINTER(HoughParams), _P]),
     ("cvb_pipeline_params_default", None, [C.POINTER(PipelineParams)]),
     ("cvb_pipeline_dev", _I, [_P, _P, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I,
                               _P, _P, _P, _P, _P, _P]),

@@ -111,7 +111,8 @@ void cvb_destroy(cvb_handle *h)
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
-                      &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks};
+                      &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks,
+                      &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->d_tables) cudaFree(h->d_tables);
@@ -264,6 +265,13 @@ void cvb_square_params_default(cvb_square_params *p)
     p->ops = CVB_SQ_PD_STATS; p->pd_blur = 5; p->cd_blur = 5;
     p->z_threshold = 2.5f; p->alpha = 0.1f; p->one_minus_alpha = (float)(1 - 0.1);
     p->initial_variance = 100.0f; p->min_variance = 10.0f;
+}
+void cvb_hough_params_default(cvb_hough_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->dp = 1.2f; p->param1 = 100; p->param2 = 25;
+    p->min_radius_ratio = 0.20; p->max_radius_ratio = 0.55;
+    p->min_radius = 0; p->max_radius = 0; p->min_dist = 0; p->min_dist_div = 3;
 }
 void cvb_pipeline_params_default(cvb_pipeline_params *p)
 {
@@ -713,6 +721,73 @@ int cvb_squares_dev(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW,
 {
     REQ_H(h);
     return squares_impl(h, boards, n, BH, BW, C, rects, n_sq, select, state, stream0, p, stats);
+}
+
+// ---- Hough circles per square ---------------------------------------------------------------------
+static int hough_check(const cvb_hough_params *p)
+{
+    CVB_REQUIRE(p != nullptr, "null Hough params");
+    CVB_REQUIRE(p->dp > 0 && p->param1 > 0 && p->param2 > 0, "dp, param1 and param2 must be positive");
+    CVB_REQUIRE(p->min_dist_div > 0 || p->min_dist > 0, "minDist must be positive");
+    return CVB_OK;
+}
+int cvb_hough_geometry(const cvb_rect *rects, int n_sq, const cvb_hough_params *p, cvb_hough_square *out)
+{
+    CVB_TRY(hough_check(p));
+    CVB_REQUIRE(rects && out && n_sq >= 1, "bad rect list");
+    for (int i = 0; i < n_sq; ++i) {
+        CVB_REQUIRE(rects[i].w >= 1 && rects[i].h >= 1, "empty square %d", i);
+        CVB_REQUIRE(cvb_host_hough_square(rects[i], *p, out + i) == CVB_OK, "minDist of square %d is not positive", i);
+    }
+    return CVB_OK;
+}
+static int hough_impl(cvb_handle *h, const uint8_t *planes, int n, int PH, int PW, const cvb_rect *rects, int n_sq,
+                      const uint8_t *select, const cvb_hough_params *p, cvb_hough_result *d_results)
+{
+    REQ_H(h); REQ_IMG(n, PH, PW);
+    CVB_REQUIRE(planes && rects && d_results, "null pointer");
+    CVB_REQUIRE(n_sq >= 1 && n_sq <= 65535, "bad rect list");
+    for (int i = 0; i < n_sq; ++i) {
+        CVB_REQUIRE(rects[i].w >= 1 && rects[i].h >= 1 && rects[i].x >= 0 && rects[i].y >= 0 &&
+                        rects[i].x + rects[i].w <= PW && rects[i].y + rects[i].h <= PH,
+                    "square %d (%d,%d %dx%d) outside the %dx%d plane", i, rects[i].x, rects[i].y, rects[i].w, rects[i].h, PW, PH);
+        CVB_REQUIRE(rects[i].w <= CVB_HOUGH_MAX_DIM && rects[i].h <= CVB_HOUGH_MAX_DIM,
+                    "square %d is %dx%d: the Hough kernel handles squares up to %d pixels a side", i, rects[i].w, rects[i].h,
+                    CVB_HOUGH_MAX_DIM);
+    }
+    std::vector<cvb_hough_square> sq(n_sq);
+    CVB_TRY(cvb_hough_geometry(rects, n_sq, p, sq.data()));
+    WS(ws_hough_sq, cvb_hough_square, n_sq, d_sq);
+    if (h->hough_cache.size() != sq.size() || memcmp(h->hough_cache.data(), sq.data(), sizeof(cvb_hough_square) * n_sq) != 0) {
+        CVB_CHECK_CUDA(cudaMemcpyAsync(d_sq, sq.data(), sizeof(cvb_hough_square) * n_sq, cudaMemcpyHostToDevice, h->stream));
+        CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+        h->hough_cache = sq;
+    }
+    uint8_t *d_sel = nullptr;
+    if (select) {
+        CVB_TRY(cvb_ws(h, h->ws_hough_sel, (size_t)n * n_sq, (void **)&d_sel));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(d_sel, select, (size_t)n * n_sq, cudaMemcpyHostToDevice, h->stream));
+    }
+    return launch_hough(h, planes, n, (size_t)PH * PW, PW, d_sq, sq.data(), n_sq, d_sel, *p, d_results);
+}
+int cvb_hough_dev(cvb_handle *h, const uint8_t *planes, int n, int PH, int PW, const cvb_rect *rects, int n_sq,
+                  const uint8_t *select, const cvb_hough_params *p, cvb_hough_result *results)
+{
+    return hough_impl(h, planes, n, PH, PW, rects, n_sq, select, p, results);
+}
+int cvb_hough_state(cvb_handle *h, cvb_state *state, int stream0, int n, const cvb_rect *rects, int n_sq,
+                    const uint8_t *select, const cvb_hough_params *p, cvb_hough_result *results_host)
+{
+    REQ_H(h);
+    CVB_REQUIRE(state != nullptr && stream0 >= 0 && n >= 1 && stream0 + n <= state->n_streams, "bad state / stream range");
+    CVB_REQUIRE(results_host != nullptr, "null pointer");
+    WS(ws_hough_res, cvb_hough_result, (size_t)n * n_sq, d_res);
+    const size_t plane = (size_t)state->BH * state->BW;
+    CVB_TRY(hough_impl(h, state->pd_cur + plane * stream0, n, state->BH, state->BW, rects, n_sq, select, p, d_res));
+    CVB_CHECK_CUDA(cudaMemcpyAsync(results_host, d_res, sizeof(cvb_hough_result) * (size_t)n * n_sq, cudaMemcpyDeviceToHost,
+                                   h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
 }
 
 // ---- whole path ----------------------------------------------------------------------------------

@@ -1,0 +1,357 @@
+// cv2.HoughCircles(gray, HOUGH_GRADIENT, ...) for a batch of small squares -- the step after the
+// per-square statistics in PieceDetector._detect_circle_unified (piece_detector.py:210-270),
+// SURVEY.md 8f rank 1.  One CTA owns one square; the whole transform lives in shared memory.
+//
+// OpenCV imgproc/src/hough.cpp (HoughCirclesGradient), restated (oracle: orc_hough_circles):
+//   A  Sobel 3x3 (replicate border), Canny(dx, dy, max(1, param1/2), param1) with L1 magnitude
+//   B  every edge pixel with a non-zero gradient walks a Q10 ray along +-gradient for the radii
+//      minRadius..maxRadius through an accumulator of 1/dp resolution; a ray stops at its first
+//      step outside.  The in-range steps of a straight ray through a box form an interval, so
+//      "step r votes" == "step minRadius and step r are inside": the rays are voted step-parallel
+//   C  centres: cells (not in accumulator row 0 / column 0) > param2, > left, >= right, > up, >= down
+//   D  per centre (one warp each): distances to the edge pixels, 10 bins per dp, best 10-bin
+//      window scanning downwards -> (radius, support); kept when support > param2
+//   E  OpenCV sorts by (support desc, radius desc, x asc, y asc) and greedily drops circles closer
+//      than minDist to a kept one == repeatedly take the best live candidate and kill its
+//      neighbourhood, which needs no sort.
+// All float steps are single IEEE operations (the library is built with -fmad=false).
+#include "cvb_device.cuh"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+static_assert(sizeof(cvb_hough_params) == 56 && sizeof(cvb_hough_square) == 40 && sizeof(cvb_hough_result) == 272,
+              "ABI struct layout (see _lib.py)");
+
+namespace {
+
+constexpr int HNT = 256;             // threads per square
+constexpr int HW_ = HNT / 32;        // warps
+
+struct HoughLayout {                 // byte offsets into dynamic shared memory (sized for the largest square of the call)
+    int off_acc, off_nz, off_bins, off_union, total;
+    int bins_pitch;                  // ints per warp
+};
+
+struct HoughMisc {
+    int nnz, ncent, kept, pad;
+    unsigned long long best[HW_];
+    float kx[CVB_HOUGH_MAX_CIRCLES], ky[CVB_HOUGH_MAX_CIRCLES];
+};
+
+CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
+{
+    // g has a one-pixel replicated border: pixel (y, x) sits at g[(y + 1) * gp + x + 1]
+    const uint8_t *p = g + y * gp + x;
+    const int a = p[0], b = p[1], c = p[2], d = p[gp], f = p[gp + 2], q = p[2 * gp], r = p[2 * gp + 1], s = p[2 * gp + 2];
+    gx = (c + 2 * f + s) - (a + 2 * d + q);
+    gy = (q + 2 * r + s) - (a + 2 * b + c);
+}
+
+__global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
+                                              const cvb_hough_square *__restrict__ squares, int n_sq,
+                                              const uint8_t *__restrict__ select, float dp, float idp, int canny_low,
+                                              int canny_high, int acc_thr, HoughLayout L,
+                                              cvb_hough_result *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ HoughMisc M;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sq = blockIdx.x, frame = blockIdx.y;
+    cvb_hough_result *res = out + (size_t)frame * n_sq + sq;
+    if (select && !select[(size_t)frame * n_sq + sq]) {
+        for (int i = tid; i < (int)(sizeof(cvb_hough_result) / 4); i += HNT) reinterpret_cast<int32_t *>(res)[i] = 0;
+        if (tid == 0) res->status = CVB_HOUGH_SKIPPED;
+        return;
+    }
+    const cvb_hough_square S = squares[sq];
+    const int w = S.w, h = S.h, gp = w + 2, npad = (h + 2) * gp;
+    const int arows = S.acc_rows, acols = S.acc_cols, astep = acols + 2, ncells = (arows + 2) * astep;
+    const int min_r = S.min_radius, max_r = S.max_radius, nbins = S.n_bins;
+
+    int32_t *acc = reinterpret_cast<int32_t *>(smem + L.off_acc);
+    uint16_t *nz = reinterpret_cast<uint16_t *>(smem + L.off_nz);
+    int *bins = reinterpret_cast<int *>(smem + L.off_bins) + warp * L.bins_pitch;
+    // early view of the union: gray (u8) | mag (u16) | map (u8)
+    uint8_t *s_g = smem + L.off_union;
+    uint16_t *s_m = reinterpret_cast<uint16_t *>(smem + L.off_union + ((npad + 3) & ~3));
+    uint8_t *s_map = smem + L.off_union + ((npad + 3) & ~3) + 2 * npad;
+    // late view: centre cells (u16) | radius (f32) | support (u16)
+    const int maxc = ncells / 2 + 1;
+    float *c_r = reinterpret_cast<float *>(smem + L.off_union);
+    uint16_t *c_idx = reinterpret_cast<uint16_t *>(smem + L.off_union + 4 * maxc);
+    uint16_t *c_sup = c_idx + maxc;
+
+    if (tid == 0) { M.nnz = 0; M.ncent = 0; M.kept = 0; }
+    for (int i = tid; i < ncells; i += HNT) acc[i] = 0;
+    // ---- A: gray with a replicated border, magnitudes with a zero border ----
+    const uint8_t *img = planes + (size_t)frame * plane_stride + (size_t)S.y * PW + S.x;
+    for (int i = tid; i < npad; i += HNT) {
+        const int ly = i / gp, lx = i - ly * gp;
+        const int y = min(max(ly - 1, 0), h - 1), x = min(max(lx - 1, 0), w - 1);
+        s_g[i] = __ldg(img + (size_t)y * PW + x);
+    }
+    __syncthreads();
+    for (int i = tid; i < npad; i += HNT) {
+        const int ly = i / gp, lx = i - ly * gp;
+        int m = 0;
+        if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
+            int gx, gy;
+            sobel_at(s_g, gp, ly - 1, lx - 1, gx, gy);
+            m = abs(gx) + abs(gy);
+        }
+        s_m[i] = (uint16_t)m;
+    }
+    __syncthreads();
+    // non-maximum suppression; map: 0 weak candidate, 1 no edge, 2 edge
+    for (int i = tid; i < npad; i += HNT) {
+        const int ly = i / gp, lx = i - ly * gp;
+        uint8_t v = 1;
+        if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
+            const int m = s_m[i];
+            if (m > canny_low) {
+                int xs, ys;
+                sobel_at(s_g, gp, ly - 1, lx - 1, xs, ys);
+                const int ax = abs(xs), ay = abs(ys) << 15;            // < 2^26
+                const int tg22x = ax * 13573, tg67x = tg22x + (ax << 16);   // < 2^27
+                bool cand;
+                if (ay < tg22x) cand = m > s_m[i - 1] && m >= s_m[i + 1];
+                else if (ay > tg67x) cand = m > s_m[i - gp] && m >= s_m[i + gp];
+                else {
+                    const int s = (xs ^ ys) < 0 ? -1 : 1;
+                    cand = m > s_m[i - gp - s] && m > s_m[i + gp + s];
+                }
+                if (cand) v = m > canny_high ? 2 : 0;
+            }
+        }
+        s_map[i] = v;
+    }
+    __syncthreads();
+    // hysteresis: grow the strong set through weak candidates until nothing changes
+    for (;;) {
+        bool mine = false;
+        for (int i = tid; i < npad; i += HNT) {
+            if (s_map[i] == 0) {
+                const bool hit = s_map[i - gp - 1] == 2 || s_map[i - gp] == 2 || s_map[i - gp + 1] == 2 || s_map[i - 1] == 2 ||
+                                 s_map[i + 1] == 2 || s_map[i + gp - 1] == 2 || s_map[i + gp] == 2 || s_map[i + gp + 1] == 2;
+                if (hit) { s_map[i] = 2; mine = true; }        // monotone 0 -> 2
+            }
+        }
+        if (!__syncthreads_or(mine)) break;
+    }
+    // ---- B: edge pixels with a gradient -> list; rays -> accumulator ----
+    for (int i0 = 0; i0 < npad; i0 += HNT) {
+        const int i = i0 + tid;
+        bool take = false;
+        int ly = 0, lx = 0;
+        if (i < npad && s_map[i] == 2) {
+            ly = i / gp; lx = i - ly * gp;
+            int gx, gy;
+            sobel_at(s_g, gp, ly - 1, lx - 1, gx, gy);
+            take = (gx | gy) != 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&M.nnz, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) nz[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)((lx - 1) | ((ly - 1) << 8));
+    }
+    __syncthreads();
+    const int nnz = M.nnz;
+    {
+        const int span = max_r - min_r + 1;
+        // one warp per ray (pixel, direction): lanes take the radius steps
+        for (int ray = warp; ray < 2 * nnz; ray += HW_) {
+            const int p = nz[ray >> 1], x = p & 255, y = p >> 8;
+            int gx, gy;
+            sobel_at(s_g, gp, y, x, gx, gy);
+            const float vx = (float)gx, vy = (float)gy;
+            const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+            int sx = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vx, idp), 1024.f), mag));
+            int sy = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vy, idp), 1024.f), mag));
+            if (ray & 1) { sx = -sx; sy = -sy; }
+            const int x0 = __float2int_rn(__fmul_rn(__fmul_rn((float)x, idp), 1024.f));
+            const int y0 = __float2int_rn(__fmul_rn(__fmul_rn((float)y, idp), 1024.f));
+            const int xs = (x0 + min_r * sx) >> 10, ys = (y0 + min_r * sy) >> 10;
+            if ((unsigned)xs >= (unsigned)acols || (unsigned)ys >= (unsigned)arows) continue;
+            for (int k = lane; k < span; k += 32) {
+                const int x2 = (x0 + (min_r + k) * sx) >> 10, y2 = (y0 + (min_r + k) * sy) >> 10;
+                if ((unsigned)x2 < (unsigned)acols && (unsigned)y2 < (unsigned)arows) atomicAdd(&acc[y2 * astep + x2], 1);
+            }
+        }
+    }
+    __syncthreads();      // gray / mag / map are dead from here on: the union switches to its late view
+    // ---- C: centres ----
+    if (nnz > 0 && nbins > 0) {
+        const int cw = acols, ch = arows;       // candidate cells: rows 1..arows, columns 1..acols of the padded array
+        for (int i0 = 0; i0 < cw * ch; i0 += HNT) {
+            const int i = i0 + tid;
+            bool take = false;
+            int cell = 0;
+            if (i < cw * ch) {
+                const int ay = i / cw + 1, ax = i - (ay - 1) * cw + 1;
+                cell = ay * astep + ax;
+                const int v = acc[cell];
+                take = v > acc_thr && v > acc[cell - 1] && v >= acc[cell + 1] && v > acc[cell - astep] && v >= acc[cell + astep];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&M.ncent, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (take) c_idx[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)cell;
+        }
+    }
+    __syncthreads();
+    const int ncent = M.ncent;
+    // ---- D: radius per centre, one warp each ----
+    const float dr = dp, fmin_r = (float)min_r;
+    const float minr2 = __fmul_rn(fmin_r, fmin_r), maxr2 = __fmul_rn((float)max_r, (float)max_r);
+    for (int c = warp; c < ncent; c += HW_) {
+        const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+        const float cx = __fmul_rn((float)ax + 0.5f, dr), cy = __fmul_rn((float)ay + 0.5f, dr);
+        for (int i = lane; i < nbins; i += 32) bins[i] = 0;
+        __syncwarp();
+        for (int k = lane; k < nnz; k += 32) {
+            const int p = nz[k];
+            const float ddx = __fsub_rn(cx, (float)(p & 255)), ddy = __fsub_rn(cy, (float)(p >> 8));
+            const float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+            if (minr2 <= r2 && r2 <= maxr2) {
+                const float t = __fmul_rn(__fdiv_rn(__fsub_rn(__fsqrt_rn(r2), fmin_r), dr), 10.f);
+                atomicAdd(&bins[min(max(__float2int_rn(t), 0), nbins - 1)], 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int max_count = 0;
+            float rbest = 0.f;
+            for (int j = nbins - 1; j > 0; j--) {
+                if (bins[j]) {
+                    const int up = j;
+                    int cur = 0;
+                    for (; j > up - 10 && j >= 0; j--) cur += bins[j];
+                    const float rcur = __fadd_rn(__fmul_rn(__fdiv_rn(__fdiv_rn((float)(up + j), 2.f), 10.f), dr), fmin_r);
+                    if (__fmul_rn((float)cur, rbest) >= __fmul_rn((float)max_count, rcur) ||
+                        (rbest < 1.1920929e-07f && cur >= max_count)) {
+                        rbest = rcur; max_count = cur;
+                    }
+                }
+            }
+            c_r[c] = rbest;
+            c_sup[c] = (uint16_t)(max_count > acc_thr ? max_count : 0);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- E: best live candidate first, then kill everything closer than minDist ----
+    const float md2 = __fmul_rn(S.min_dist, S.min_dist);
+    for (;;) {
+        unsigned long long best = 0;
+        for (int c = tid; c < ncent; c += HNT) {
+            const unsigned sup = c_sup[c];
+            if (sup) {
+                const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+                const unsigned long long key = ((unsigned long long)sup << 48) | ((unsigned long long)__float_as_uint(c_r[c]) << 16) |
+                                               ((unsigned long long)(255 - ax) << 8) | (unsigned long long)(255 - ay);
+                best = key > best ? key : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) M.best[warp] = best;
+        __syncthreads();
+        best = M.best[0];
+#pragma unroll
+        for (int i = 1; i < HW_; ++i) best = M.best[i] > best ? M.best[i] : best;
+        if (best == 0) break;
+        const int bx = 255 - (int)((best >> 8) & 255), by = 255 - (int)(best & 255);
+        const float kx = __fmul_rn((float)bx + 0.5f, dr), ky = __fmul_rn((float)by + 0.5f, dr);
+        if (tid == 0) {
+            const int k = M.kept++;
+            if (k < CVB_HOUGH_MAX_CIRCLES) {
+                res->xyr[k][0] = kx; res->xyr[k][1] = ky; res->xyr[k][2] = __uint_as_float((unsigned)(best >> 16));
+                res->support[k] = (int)(best >> 48);
+            }
+        }
+        for (int c = tid; c < ncent; c += HNT) {
+            if (c_sup[c]) {
+                const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+                const float ex = __fsub_rn(kx, __fmul_rn((float)ax + 0.5f, dr)), ey = __fsub_rn(ky, __fmul_rn((float)ay + 0.5f, dr));
+                if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < md2) c_sup[c] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int kept = M.kept;
+        res->count = kept; res->n_edges = nnz; res->n_centers = ncent; res->status = CVB_HOUGH_OK;
+        for (int k = kept; k < CVB_HOUGH_MAX_CIRCLES; ++k) {
+            res->xyr[k][0] = res->xyr[k][1] = res->xyr[k][2] = 0.f;
+            res->support[k] = 0;
+        }
+    }
+}
+
+}  // namespace
+
+// Per-square geometry of one cv2.HoughCircles call (hough.cpp: HoughCircles / HoughCirclesGradient argument handling)
+int cvb_host_hough_square(const cvb_rect &r, const cvb_hough_params &p, cvb_hough_square *out)
+{
+    const int md = std::min(r.w, r.h);
+    int min_r = p.min_radius_ratio >= 0 ? (int)((double)md * p.min_radius_ratio) : p.min_radius;      // piece_detector.py:225
+    int max_r = p.max_radius_ratio >= 0 ? (int)((double)md * p.max_radius_ratio) : p.max_radius;      // piece_detector.py:226
+    const float min_dist = p.min_dist_div > 0 ? (float)(md / p.min_dist_div) : p.min_dist;            // piece_detector.py:236
+    if (!(min_dist > 0)) return CVB_ERR_INVALID;
+    if (min_r < 0) min_r = 0;
+    if (max_r <= 0) max_r = std::max(r.w, r.h);
+    else if (max_r <= min_r) max_r = min_r + 2;
+    const float dp = p.dp < 1.f ? 1.f : p.dp, idp = 1.f / dp;
+    out->x = r.x; out->y = r.y; out->w = r.w; out->h = r.h;
+    out->min_radius = min_r; out->max_radius = max_r; out->min_dist = min_dist;
+    out->acc_rows = (int)std::ceil(r.h * idp);
+    out->acc_cols = (int)std::ceil(r.w * idp);
+    out->n_bins = (int)std::lrint((float)((float)(max_r - min_r) / dp * 10));
+    return CVB_OK;
+}
+
+int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_stride, int PW, const cvb_hough_square *d_squares,
+                 const cvb_hough_square *squares, int n_sq, const uint8_t *d_select, const cvb_hough_params &p,
+                 cvb_hough_result *out)
+{
+    const float dp = p.dp < 1.f ? 1.f : p.dp, idp = 1.f / dp;
+    const int canny_high = (int)std::lrint(p.param1), acc_thr = (int)std::lrint(p.param2);
+    const int canny_low = std::max(1, canny_high / 2);
+    // shared-memory layout for the largest square of the list
+    size_t acc_b = 0, nz_b = 0, bins_i = 0, uni_b = 0;
+    for (int i = 0; i < n_sq; ++i) {
+        const cvb_hough_square &s = squares[i];
+        const size_t npad = (size_t)(s.h + 2) * (s.w + 2), ncells = (size_t)(s.acc_rows + 2) * (s.acc_cols + 2);
+        acc_b = std::max(acc_b, ncells * 4);
+        nz_b = std::max(nz_b, (size_t)s.h * s.w * 2);
+        bins_i = std::max(bins_i, (size_t)std::max(s.n_bins, 1));
+        const size_t early = ((npad + 3) & ~(size_t)3) + 3 * npad, late = 8 * (ncells / 2 + 1);
+        uni_b = std::max(uni_b, std::max(early, late));
+    }
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    HoughLayout L;
+    L.off_acc = 0;
+    L.off_nz = (int)up16(acc_b);
+    L.off_bins = L.off_nz + (int)up16(nz_b);
+    L.bins_pitch = (int)((bins_i + 3) & ~(size_t)3);
+    L.off_union = L.off_bins + (int)up16((size_t)L.bins_pitch * 4 * HW_);
+    L.total = L.off_union + (int)up16(uni_b);
+    CVB_REQUIRE(L.total <= 220 * 1024, "Hough workspace of %d bytes per square exceeds shared memory", L.total);
+    const void *fn = (const void *)k_hough;
+    auto it = h->squares_smem_attr.find(fn);
+    if (it == h->squares_smem_attr.end() || it->second < (size_t)L.total) {
+        CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        h->squares_smem_attr[fn] = (size_t)L.total;
+    }
+    PROF(h, "k_hough");
+    k_hough<<<dim3(n_sq, n), HNT, L.total, h->stream>>>(planes, plane_stride, PW, d_squares, n_sq, d_select, dp, idp, canny_low,
+                                                        canny_high, acc_thr, L, out);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}

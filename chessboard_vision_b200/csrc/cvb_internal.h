@@ -86,6 +86,9 @@ struct cvb_handle {
     int chunk_frames = 8;
     // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
     DevBuf ws_masks;
+    // Hough: staged per-square geometry (content-compared), select bytes, results
+    std::vector<cvb_hough_square> hough_cache;
+    DevBuf ws_hough_sq, ws_hough_sel, ws_hough_res;
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 };
@@ -157,3 +160,9 @@ int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, 
                    const uint8_t *d_select, cvb_state *st, int stream0, const cvb_square_params &p,
                    const int *pd_q, const int *cd_q, cvb_square_stats *stats);
 int launch_state_reset(cvb_handle *h, cvb_state *s, int stream);
+
+// ---- cvb_hough.cu ---------------------------------------------------------------------
+int cvb_host_hough_square(const cvb_rect &r, const cvb_hough_params &p, cvb_hough_square *out);
+int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_stride, int PW, const cvb_hough_square *d_squares,
+                 const cvb_hough_square *squares, int n_sq, const uint8_t *d_select, const cvb_hough_params &p,
+                 cvb_hough_result *out);

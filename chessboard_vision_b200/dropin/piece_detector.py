@@ -8,8 +8,10 @@ returns integer sums and this class turns them into the reference's floats
 and flags.  The temporal logic (history vote, caching, gating: :99-122,
 :348-440) is scalar Python and stays on the host, as in the reference.
 
-Out of the hot path: `cv2.HoughCircles`
-(:210-270) keeps running in host OpenCV, on the gray square the GPU produced.
+`cv2.HoughCircles` (:210-270) runs on the GPU too: one CTA per
+square on the gray+blur squares the statistics launch left on the device, for all
+squares that need it in one launch, bit-identical to OpenCV's circle list; the
+choice of the circle nearest the square centre (:245-268) stays on the host.
 """
 import json
 import os
@@ -70,6 +72,15 @@ class PieceDetector:
             self.reference_squares.device_changed([k for k in keys if k in set(set_ref_keys)])
         return out
 
+    def _hough_batch(self, stats, keys):
+        """One Hough launch for the squares of `keys` that pass the std gate (piece_detector.py:305)."""
+        need = [k for k in keys if not hostapi.std_below(stats[k], 15)]
+        return self._run.hough(need, self._hough_params()) if need else {}
+
+    def _shape_of(self, pos):
+        x, y, w, h = self._run.layout[pos]
+        return np.empty((h, w), np.uint8)
+
     def _gray_squares(self, keys=None):
         plane = self._run.current_plane()
         lay = self._run.layout
@@ -80,9 +91,9 @@ class PieceDetector:
         self.reference_squares.clear()
         self.cached_results.clear()
         stats = self._stats(squares_dict, set_ref_keys=list(squares_dict.keys()))
-        grays = self._gray_squares()
+        circles = self._hough_batch(stats, list(squares_dict.keys()))
         for pos in squares_dict:
-            self.cached_results[pos] = self._detect_from(stats[pos], grays[pos])
+            self.cached_results[pos] = self._detect_from(stats[pos], self._shape_of(pos), circles.get(pos))
 
     def update_references(self, squares_dict):
         self._stats(squares_dict, set_ref_keys=list(squares_dict.keys()), stats=False)
@@ -143,23 +154,22 @@ class PieceDetector:
         p = self._e.square_params(ops=SQ_PD_STATS, pd_blur=1)
         return self._e.squares(g, [(0, 0, g.shape[1], g.shape[0])], p)[0, 0]
 
-    def _detect_circle_unified(self, gray):
-        """piece_detector.py:210-270 -- Hough transform.  Outside the hot path by design (SURVEY.md 8f
-        rank 1): it runs in host OpenCV on the gray square the GPU produced.
-        -> (found, centre, radius, 'hough' | 'tower_top')"""
-        try:
-            import cv2
-        except ImportError as e:   # pragma: no cover
-            raise NotImplementedError("cv2.HoughCircles is outside the B200 hot path and OpenCV is not installed") from e
-        h, w = gray.shape
+    def _hough_params(self):
+        """The arguments of piece_detector.py:225-241."""
+        return self._e.hough_params(dp=1.2, param1=getattr(self, 'hough_param1', 100), param2=getattr(self, 'hough_param2', 25),
+                                    min_radius_ratio=self.min_radius_ratio, max_radius_ratio=self.max_radius_ratio,
+                                    min_dist_div=3)
+
+    @staticmethod
+    def _pick_circle(rec, h, w):
+        """piece_detector.py:243-270 on one Hough record -> (found, centre, radius, 'hough' | 'tower_top')"""
+        count = int(rec["count"])
+        if count > _lib.HOUGH_MAX_CIRCLES:
+            raise RuntimeError("%d circles in one square: more than the %d the Hough kernel stores"
+                               % (count, _lib.HOUGH_MAX_CIRCLES))
         md = min(h, w)
-        circles = cv2.HoughCircles(np.ascontiguousarray(gray), cv2.HOUGH_GRADIENT, dp=1.2, minDist=md // 3,
-                                   param1=getattr(self, 'hough_param1', 100), param2=getattr(self, 'hough_param2', 25),
-                                   minRadius=int(md * self.min_radius_ratio), maxRadius=int(md * self.max_radius_ratio))
-        if circles is None or len(circles[0]) == 0:
-            return False, None, None, None
         best, best_d = None, float('inf')
-        for c in circles[0]:
+        for c in rec["xyr"][:count]:
             d = np.sqrt((c[0] - w // 2) ** 2 + (c[1] - h // 2) ** 2)
             if d < md * 0.3 and d < best_d:
                 best, best_d = c, d
@@ -168,13 +178,27 @@ class PieceDetector:
         r = int(best[2])
         return True, (int(best[0]), int(best[1])), r, ('tower_top' if r < md * 0.20 else 'hough')
 
+    def _detect_circle_unified(self, gray):
+        """piece_detector.py:210-270 -- cv2.HoughCircles on one gray square, on the GPU.
+        -> (found, centre, radius, 'hough' | 'tower_top')"""
+        g = np.ascontiguousarray(gray, np.uint8)
+        h, w = g.shape
+        if min(h, w) // 3 < 1:
+            raise ValueError("square of %dx%d: minDist = min_dim // 3 must be positive (cv2.HoughCircles asserts)" % (h, w))
+        rec = self._e.hough(g, [(0, 0, w, h)], self._hough_params())[0, 0]
+        return self._pick_circle(rec, h, w)
+
     # -- detection (piece_detector.py:272-346) --
-    def _detect_from(self, st, gray):
+    def _detect_from(self, st, gray, hough_rec=None):
+        """`gray` is only used for its shape when the square's Hough record is already there."""
         h, w = gray.shape
         result = _empty_result()
         if hostapi.std_below(st, 15):
             return result
-        found, center, radius, kind = self._detect_circle_unified(gray)
+        if hough_rec is not None:
+            found, center, radius, kind = self._pick_circle(hough_rec, h, w)
+        else:
+            found, center, radius, kind = self._detect_circle_unified(gray)
         if found:
             result.update(has_piece=True, center=center, radius=radius, method=kind,
                           confidence=0.9 if kind == 'hough' else 0.75)
@@ -201,7 +225,7 @@ class PieceDetector:
         if not squares_dict:
             return results, visual_changes
         stats = self._stats(squares_dict)
-        grays = None
+        plan = {}
         for pos in squares_dict:
             st = stats[pos]
             changed = (not st["has_ref"]) or hostapi.mean_abs_diff(st) > self.change_threshold
@@ -210,10 +234,13 @@ class PieceDetector:
             should_process = squares_to_check is not None and pos in squares_to_check
             if not should_process and (squares_to_check is None or use_delta):
                 should_process = pos not in self.cached_results or changed
-            if should_process or pos not in self.cached_results:
-                if grays is None:
-                    grays = self._gray_squares()
-                raw = self._detect_from(st, grays[pos])
+            plan[pos] = (should_process, should_process or pos not in self.cached_results)
+        # every square that is detected this frame goes through one Hough launch
+        circles = self._hough_batch(stats, [pos for pos, (_, detect) in plan.items() if detect])
+        for pos in squares_dict:
+            should_process, detect = plan[pos]
+            if detect:
+                raw = self._detect_from(stats[pos], self._shape_of(pos), circles.get(pos))
                 self.cached_results[pos] = raw.copy()
             else:
                 raw = self.cached_results[pos].copy()

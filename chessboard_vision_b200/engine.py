@@ -15,7 +15,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (ColorProfile, EnhanceParams, PipelineParams, Rect, SquareParams, SquareStats, check,
+from ._lib import (ColorProfile, EnhanceParams, HoughParams, HoughResult, HoughSquare, PipelineParams, Rect, SquareParams,
+                   SquareStats, check, HOUGH_MAX_CIRCLES,
                    SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
 
 STATS_DTYPE = np.dtype([("n", "<i4"), ("has_ref", "<i4"), ("sum", "<u4"), ("sad", "<u4"), ("sumsq", "<u8"),
@@ -23,6 +24,12 @@ STATS_DTYPE = np.dtype([("n", "<i4"), ("has_ref", "<i4"), ("sum", "<u4"), ("sad"
                         ("ring_sum", "<u4", (4,)), ("ring_cnt", "<u4", (4,)),
                         ("cd_changed", "<i4"), ("cd_zmax", "<f4"), ("cd_valid", "<i4"), ("reserved", "<i4", (11,))])
 assert STATS_DTYPE.itemsize == C.sizeof(SquareStats)
+HOUGH_DTYPE = np.dtype([("count", "<i4"), ("n_edges", "<i4"), ("n_centers", "<i4"), ("status", "<i4"),
+                        ("xyr", "<f4", (HOUGH_MAX_CIRCLES, 3)), ("support", "<i4", (HOUGH_MAX_CIRCLES,))])
+HOUGH_SQUARE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("min_radius", "<i4"),
+                               ("max_radius", "<i4"), ("acc_rows", "<i4"), ("acc_cols", "<i4"), ("n_bins", "<i4"),
+                               ("min_dist", "<f4")])
+assert HOUGH_DTYPE.itemsize == C.sizeof(HoughResult) and HOUGH_SQUARE_DTYPE.itemsize == C.sizeof(HoughSquare)
 
 
 class DevArray:
@@ -508,6 +515,74 @@ class Engine:
         if tmp:
             src.free()
         return out
+
+    # -- Hough circles per square (piece_detector.py:210-270) ------------------------------------------
+    def hough_params(self, dp=1.2, param1=100, param2=25, min_radius_ratio=0.20, max_radius_ratio=0.55,
+                     min_dist_div=3, min_radius=None, max_radius=None, min_dist=None):
+        """The arguments of the reference's cv2.HoughCircles call.  By default the radii and minDist
+        follow each square (`int(min_dim * ratio)`, `min_dim // 3`); explicit `min_radius`,
+        `max_radius`, `min_dist` give cv2.HoughCircles' own arguments instead."""
+        p = HoughParams()
+        self.lib.cvb_hough_params_default(C.byref(p))
+        p.dp = float(dp); p.param1 = float(param1); p.param2 = float(param2)
+        p.min_radius_ratio = float(min_radius_ratio); p.max_radius_ratio = float(max_radius_ratio)
+        p.min_dist_div = int(min_dist_div)
+        if min_radius is not None:
+            p.min_radius_ratio = -1.0; p.min_radius = int(min_radius)
+        if max_radius is not None:
+            p.max_radius_ratio = -1.0; p.max_radius = int(max_radius)
+        if min_dist is not None:
+            p.min_dist_div = 0; p.min_dist = float(min_dist)
+        return p
+
+    def hough_geometry(self, rects, params):
+        ra = _rect_array(rects)
+        out = np.zeros(len(rects), HOUGH_SQUARE_DTYPE)
+        check(self.lib.cvb_hough_geometry(C.cast(ra, C.c_void_p), len(rects), C.byref(params), out.ctypes.data))
+        return out
+
+    @staticmethod
+    def _hough_select(select, n, n_sq):
+        if select is None:
+            return None
+        sel = np.ascontiguousarray(select, np.uint8)
+        if sel.size == n_sq and n > 1:
+            sel = np.ascontiguousarray(np.broadcast_to(sel.reshape(1, n_sq), (n, n_sq)))
+        assert sel.size == n * n_sq
+        return sel
+
+    def hough(self, planes, rects, params=None, select=None):
+        """planes: (PH,PW) / (n,PH,PW) u8 gray (numpy or DevArray) -> structured array (n, n_sq) of HOUGH_DTYPE:
+        cv2.HoughCircles of every selected square, circles in OpenCV's order."""
+        params = params or self.hough_params()
+        shape = planes.shape
+        n, PH, PW = (1, shape[0], shape[1]) if len(shape) == 2 else shape
+        src, tmp = self._in(planes)
+        ra = _rect_array(rects)
+        sel = self._hough_select(select, n, len(rects))
+        res = self.empty((n, len(rects)), HOUGH_DTYPE)
+        check(self.lib.cvb_hough_dev(self.h, src.ptr, n, PH, PW, C.cast(ra, C.c_void_p), len(rects),
+                                     sel.ctypes.data if sel is not None else None, C.byref(params), res.ptr))
+        out = res.get(); res.free()
+        if tmp:
+            src.free()
+        return out
+
+    def hough_state(self, state, rects, params=None, stream0=0, n=1, select=None):
+        """The same on the state's last gray+blur squares (plane PLANE_PD_CUR) of n stream slots."""
+        params = params or self.hough_params()
+        ra = _rect_array(rects)
+        sel = self._hough_select(select, n, len(rects))
+        out = np.zeros((n, len(rects)), HOUGH_DTYPE)
+        check(self.lib.cvb_hough_state(self.h, state.ptr, int(stream0), int(n), C.cast(ra, C.c_void_p), len(rects),
+                                       sel.ctypes.data if sel is not None else None, C.byref(params), out.ctypes.data))
+        return out
+
+    @staticmethod
+    def hough_circles(rec):
+        """One HOUGH_DTYPE record -> what cv2.HoughCircles returns: (1, k, 3) f32 or None."""
+        k = min(int(rec["count"]), HOUGH_MAX_CIRCLES)
+        return rec["xyr"][:k].reshape(1, k, 3).copy() if k else None
 
     # -- whole path ----------------------------------------------------------------------------------
     def pipeline_params(self, enhance=None, squares=None, warp_enhanced=True, board_size=620):

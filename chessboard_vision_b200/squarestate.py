@@ -168,3 +168,13 @@ class SquareRunner:
     def current_plane(self):
         """gray+blur squares of the last launch (PLANE_PD_CUR)."""
         return self.state.get(0, _lib.PLANE_PD_CUR)
+
+    def hough(self, keys, params):
+        """cv2.HoughCircles on the gray+blur squares of the last launch, for `keys` only -> {key: record}."""
+        order = [k for k in self._order if k in self.layout]
+        want = set(keys)
+        select = np.array([1 if k in want else 0 for k in order], np.uint8)
+        if not select.any():
+            return {}
+        out = self.e.hough_state(self.state, [self.layout[k] for k in order], params, 0, 1, select)
+        return {k: out[0, i] for i, k in enumerate(order) if k in want}

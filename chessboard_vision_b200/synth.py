@@ -60,3 +60,40 @@ def board_with_pieces(seed=11, base_seed=7, size=620):
         col = rng.integers(0, 256, 3)
         out[((xx - cx) ** 2 + (yy - cy) ** 2) <= rad * rad] = col
     return board, out
+
+
+def shape_atlas(seed=0, n_squares=48, min_side=8, max_side=128, plane_w=1024):
+    """A gray plane packed with `n_squares` rectangles of random size, each holding random discs,
+    rings and bars on a flat background plus noise and a 3x3 box blur -- varied input for the
+    Hough-circle stage.  -> (plane u8, [(x, y, w, h), ...])"""
+    rng = np.random.default_rng(seed)
+    rects, x, y, row_h = [], 0, 0, 0
+    for _ in range(n_squares):
+        w, h = int(rng.integers(min_side, max_side + 1)), int(rng.integers(min_side, max_side + 1))
+        if x + w > plane_w:
+            x, y, row_h = 0, y + row_h, 0
+        rects.append((x, y, w, h))
+        x, row_h = x + w, max(row_h, h)
+    plane = np.zeros((y + row_h, plane_w), np.uint8)
+    for (x, y, w, h) in rects:
+        img = np.full((h, w), float(rng.integers(40, 200)))
+        yy, xx = np.ogrid[:h, :w]
+        for _ in range(int(rng.integers(0, 4))):
+            cx, cy = int(rng.integers(0, w)), int(rng.integers(0, h))
+            rad = int(rng.integers(3, max(4, min(h, w) // 2)))
+            d2 = (xx - cx) ** 2 + (yy - cy) ** 2
+            mask = d2 <= rad * rad
+            if rng.random() < 0.3:
+                mask &= d2 >= max(rad - 2, 0) ** 2
+            img[mask] = float(rng.integers(0, 256))
+        if rng.random() < 0.3:
+            x0, x1 = sorted(int(v) for v in rng.integers(0, w, 2))
+            y0, y1 = sorted(int(v) for v in rng.integers(0, h, 2))
+            img[y0:y1 + 1, x0:x1 + 1] = float(rng.integers(0, 256))
+        img += rng.normal(0, float(rng.choice([0, 2, 8, 20])), img.shape)
+        img = np.clip(img, 0, 255)
+        if rng.random() < 0.7:
+            p = np.pad(img, 1, mode="edge")
+            img = sum(p[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)) / 9.0
+        plane[y:y + h, x:x + w] = img.astype(np.uint8)
+    return plane, rects

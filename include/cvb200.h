@@ -246,6 +246,57 @@ int cvb_state_set(cvb_handle *h, cvb_state *s, int stream, int plane, const void
 /* forget PD references / CD model of one stream slot (-1: all)               */
 int cvb_state_reset(cvb_handle *h, cvb_state *s, int stream);
 
+/* ---- PieceDetector._detect_circle_unified: cv2.HoughCircles per square ------------- */
+/* cv2.HoughCircles(gray, HOUGH_GRADIENT, dp, minDist, param1, param2, minRadius,
+ * maxRadius) on every selected square of n gray planes  piece_detector.py:210-270.
+ * One CTA per square, the whole transform in shared memory; squares up to
+ * CVB_HOUGH_MAX_DIM pixels a side.  Bit-identical to OpenCV 4.13 (circle list,
+ * order, f32 values).                                                            */
+#define CVB_HOUGH_MAX_CIRCLES 16   /* circles stored per square (minDist = side/3 allows <= 16) */
+#define CVB_HOUGH_MAX_DIM     128
+enum { CVB_HOUGH_OK = 0, CVB_HOUGH_SKIPPED = 1 };
+typedef struct {
+    float  dp;                  /* 1.2 (values < 1 are raised to 1, as OpenCV does)   piece_detector.py:235 */
+    float  min_dist;            /* used when min_dist_div <= 0                            */
+    double param1;              /* Canny high threshold, 100   piece_detector.py:230      */
+    double param2;              /* accumulator / support threshold, 25   :229             */
+    double min_radius_ratio;    /* minRadius = (int)(min(h,w) * ratio), 0.20   :225; < 0: use min_radius */
+    double max_radius_ratio;    /* maxRadius = (int)(min(h,w) * ratio), 0.55   :226; < 0: use max_radius */
+    int    min_radius, max_radius;
+    int    min_dist_div;        /* 3: minDist = min(h,w) / 3   :236                       */
+    int    reserved;
+} cvb_hough_params;
+void cvb_hough_params_default(cvb_hough_params *p);
+/* what one square's call resolves to (OpenCV's argument handling included) */
+typedef struct {
+    int32_t x, y, w, h;
+    int32_t min_radius, max_radius;
+    int32_t acc_rows, acc_cols; /* ceil(h / dp), ceil(w / dp)                             */
+    int32_t n_bins;             /* radius histogram bins, 10 per dp                       */
+    float   min_dist;
+} cvb_hough_square;
+typedef struct {
+    int32_t count;              /* circles after the minDist filter (may exceed the 16 stored) */
+    int32_t n_edges;            /* Canny edge pixels that voted                           */
+    int32_t n_centers;          /* accumulator maxima examined                            */
+    int32_t status;             /* CVB_HOUGH_OK / CVB_HOUGH_SKIPPED                       */
+    float   xyr[CVB_HOUGH_MAX_CIRCLES][3];   /* (x, y, radius) in OpenCV's order          */
+    int32_t support[CVB_HOUGH_MAX_CIRCLES];  /* edge pixels in the winning radius window  */
+} cvb_hough_result;
+/* host only: rects -> per-square geometry */
+int cvb_hough_geometry(const cvb_rect *rects, int n_sq, const cvb_hough_params *p, cvb_hough_square *out);
+/* planes: DEVICE n x PH x PW u8 (gray + blur, e.g. state plane 3); rects HOST
+ * (shared by the batch); select: HOST n*n_sq bytes or NULL (all);
+ * results: DEVICE n*n_sq.                                                        */
+int cvb_hough_dev(cvb_handle *h, const uint8_t *planes, int n, int PH, int PW,
+                  const cvb_rect *rects, int n_sq, const uint8_t *select,
+                  const cvb_hough_params *p, cvb_hough_result *results);
+/* the same on the pd_cur planes (last gray + blur of every square) of the state
+ * slots stream0 .. stream0+n-1; results: HOST n*n_sq; synchronises.              */
+int cvb_hough_state(cvb_handle *h, cvb_state *state, int stream0, int n,
+                    const cvb_rect *rects, int n_sq, const uint8_t *select,
+                    const cvb_hough_params *p, cvb_hough_result *results_host);
+
 /* ---- the whole hot path for a batch ------------------------------------------------ */
 typedef struct {
     cvb_enhance_params enhance;

@@ -911,6 +911,149 @@ ORC_API void orc_canny(const u8 *src, int H, int W, double low_thresh, double hi
     free(dx); free(dy); free(mag); free(map); free(stack);
 }
 
+/* ------------------------------------------------------------------------ */
+/* cv2.HoughCircles(gray, HOUGH_GRADIENT, dp, minDist, param1, param2,        */
+/* minRadius, maxRadius) -- reference call piece_detector.py:232-241.         */
+/* OpenCV imgproc/src/hough.cpp (HoughCirclesGradient), restated:             */
+/*  1. Sobel 3x3 (replicate border) and Canny(dx, dy, max(1, param1/2),       */
+/*     param1), L1 magnitude;                                                 */
+/*  2. every edge pixel with a non-zero gradient votes along +-gradient for   */
+/*     the radii minRadius..maxRadius in an accumulator of 1/dp resolution    */
+/*     (Q10 fixed-point ray, stops at the first step outside);                */
+/*  3. centres: accumulator cells (not in row 0 / column 0) > param2 that    */
+/*     are local maxima (> left, >= right, > up, >= down);                    */
+/*  4. per centre: distances to all edge pixels, histogram with 10 bins per   */
+/*     dp, best 10-bin window scanning downwards -> (radius, support);        */
+/*     kept when support > param2;                                            */
+/*  5. sort by (support desc, radius desc, x asc, y asc); greedy removal of   */
+/*     circles closer than minDist to a kept one.                             */
+/* All float steps are f32 and unfused, as in the SSE-baseline build.         */
+/* out: up to max_out rows of (x, y, r, support); returns the circle count    */
+/* (may exceed max_out; only the first max_out are stored), -1 on bad input.  */
+/* ------------------------------------------------------------------------ */
+typedef struct { float x, y, r; int support; } orc_circle;
+static int circle_before(const orc_circle *a, const orc_circle *b)
+{
+    if (a->support != b->support) return a->support > b->support;
+    if (a->r != b->r) return a->r > b->r;
+    if (a->x != b->x) return a->x < b->x;
+    return a->y < b->y;
+}
+static int circle_cmp(const void *pa, const void *pb)
+{
+    const orc_circle *a = (const orc_circle *)pa, *b = (const orc_circle *)pb;
+    return circle_before(a, b) ? -1 : circle_before(b, a) ? 1 : 0;
+}
+ORC_API int orc_hough_circles(const u8 *gray, int H, int W, long stride, double dp_d, double min_dist_d,
+                              double param1, double param2, int min_radius, int max_radius,
+                              float *out, int max_out, int32_t *info)
+{
+    if (H < 1 || W < 1 || dp_d <= 0 || min_dist_d <= 0 || param1 <= 0 || param2 <= 0) return -1;
+    const float dp = (float)dp_d < 1.f ? 1.f : (float)dp_d;
+    const float min_dist = (float)min_dist_d;
+    const int canny_thr = (int)lrint(param1), acc_thr = (int)lrint(param2);
+    if (min_radius < 0) min_radius = 0;
+    if (max_radius <= 0) max_radius = H > W ? H : W;
+    else if (max_radius <= min_radius) max_radius = min_radius + 2;
+    const long n = (long)H * W;
+    u8 *g = (u8 *)malloc(n), *edges = (u8 *)malloc(n);
+    for (int y = 0; y < H; y++) memcpy(g + (long)y * W, gray + y * stride, W);
+    orc_canny(g, H, W, canny_thr / 2 > 1 ? canny_thr / 2 : 1, canny_thr, edges);
+    const float idp = 1.f / dp;
+    const int arows = (int)ceilf(H * idp), acols = (int)ceilf(W * idp), astep = acols + 2;
+    int32_t *acc = (int32_t *)calloc((long)(arows + 2) * astep, 4);
+    int32_t *nz = (int32_t *)malloc(n * 4);
+    long nnz = 0;
+    const int ONE = 1 << 10;
+#define S(yy, xx) ((int)g[(long)((yy) < 0 ? 0 : (yy) >= H ? H - 1 : (yy)) * W + ((xx) < 0 ? 0 : (xx) >= W ? W - 1 : (xx))])
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            if (!edges[(long)y * W + x]) continue;
+            const int gx = (S(y - 1, x + 1) + 2 * S(y, x + 1) + S(y + 1, x + 1)) - (S(y - 1, x - 1) + 2 * S(y, x - 1) + S(y + 1, x - 1));
+            const int gy = (S(y + 1, x - 1) + 2 * S(y + 1, x) + S(y + 1, x + 1)) - (S(y - 1, x - 1) + 2 * S(y - 1, x) + S(y - 1, x + 1));
+            if (gx == 0 && gy == 0) continue;
+            const float vx = (float)gx, vy = (float)gy;
+            const float mag = sqrtf(vx * vx + vy * vy);
+            if (mag < 1.0f) continue;
+            nz[nnz++] = (y << 16) | x;
+            int sx = (int)lrintf((vx * idp) * ONE / mag), sy = (int)lrintf((vy * idp) * ONE / mag);
+            const int x0 = (int)lrintf((x * idp) * ONE), y0 = (int)lrintf((y * idp) * ONE);
+            for (int k = 0; k < 2; k++) {
+                int x1 = x0 + min_radius * sx, y1 = y0 + min_radius * sy;
+                for (int r = min_radius; r <= max_radius; x1 += sx, y1 += sy, r++) {
+                    const int x2 = x1 >> 10, y2 = y1 >> 10;
+                    if ((unsigned)x2 >= (unsigned)acols || (unsigned)y2 >= (unsigned)arows) break;
+                    acc[(long)(y2 + 1) * astep + x2 + 1]++;
+                }
+                sx = -sx; sy = -sy;
+            }
+        }
+#undef S
+    int count = 0, ncenters = 0;
+    orc_circle *est = NULL;
+    if (nnz) {
+        const float dr = dp;
+        const int per = 10;
+        const int nbins = (int)lrintf((max_radius - min_radius) / dr * per);
+        int *bins = (int *)malloc((nbins > 0 ? nbins : 1) * sizeof(int));
+        const float minr2 = (float)min_radius * min_radius, maxr2 = (float)max_radius * max_radius;
+        long cap = 64, nest = 0;
+        est = (orc_circle *)malloc(cap * sizeof(orc_circle));
+        /* hough.cpp votes into the padded accumulator without an offset and scans its interior, so
+         * the cells of accumulator row 0 / column 0 are neighbours only, never centres */
+        for (int ay = 2; ay <= arows; ay++)
+            for (int ax = 2; ax <= acols; ax++) {
+                const int32_t *a = acc + (long)ay * astep + ax;
+                if (!(a[0] > acc_thr && a[0] > a[-1] && a[0] >= a[1] && a[0] > a[-astep] && a[0] >= a[astep])) continue;
+                ncenters++;
+                const float cx = ((ax - 1) + 0.5f) * dr, cy = ((ay - 1) + 0.5f) * dr;
+                int max_count = 0; float rbest = 0;
+                for (int i = 0; i < nbins; i++) bins[i] = 0;
+                int used = 0;
+                for (long k = 0; k < nnz && nbins > 0; k++) {
+                    const float ddx = cx - (float)(nz[k] & 0xffff), ddy = cy - (float)(nz[k] >> 16);
+                    const float a2 = ddx * ddx, b2 = ddy * ddy, r2 = a2 + b2;
+                    if (minr2 <= r2 && r2 <= maxr2) {
+                        int b = (int)lrintf((sqrtf(r2) - min_radius) / dr * per);
+                        b = b < 0 ? 0 : b > nbins - 1 ? nbins - 1 : b;
+                        bins[b]++; used++;
+                    }
+                }
+                if (used)
+                    for (int j = nbins - 1; j > 0; j--)
+                        if (bins[j]) {
+                            const int up = j; int cur = 0;
+                            for (; j > up - per && j >= 0; j--) cur += bins[j];
+                            const float rcur = (up + j) / 2.f / per * dr + min_radius;
+                            if ((cur * rbest >= max_count * rcur) || (rbest < FLT_EPSILON && cur >= max_count)) { rbest = rcur; max_count = cur; }
+                        }
+                if (max_count > acc_thr) {
+                    if (nest == cap) { cap *= 2; est = (orc_circle *)realloc(est, cap * sizeof(orc_circle)); }
+                    est[nest].x = cx; est[nest].y = cy; est[nest].r = rbest; est[nest].support = max_count; nest++;
+                }
+            }
+        qsort(est, nest, sizeof(orc_circle), circle_cmp);
+        /* RemoveOverlaps: in place, keeps the first of any two closer than minDist */
+        long kept = nest ? 1 : 0;
+        for (long i = 1; i < nest; i++) {
+            int ok = 1;
+            for (long k = 0; k < kept && ok; k++) {
+                const float ex = est[k].x - est[i].x, ey = est[k].y - est[i].y;
+                if (ex * ex + ey * ey < min_dist * min_dist) ok = 0;
+            }
+            if (ok) est[kept++] = est[i];
+        }
+        count = (int)kept;
+        for (long i = 0; i < kept && i < max_out; i++) {
+            out[4 * i] = est[i].x; out[4 * i + 1] = est[i].y; out[4 * i + 2] = est[i].r; out[4 * i + 3] = (float)est[i].support;
+        }
+        free(bins);
+    }
+    if (info) { info[0] = (int32_t)nnz; info[1] = ncenters; }
+    free(est); free(g); free(edges); free(acc); free(nz);
+    return count;
+}
+
 /* find_internal_lines (grid_extractor.py:83-110): border 0, seven window arg-max positions, border `length` */
 static void internal_lines(const uint64_t *proj, int length, int32_t *lines)
 {

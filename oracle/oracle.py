@@ -333,6 +333,24 @@ def canny(gray_u8, low=50, high=150):
     return out
 
 
+def hough_circles(gray_u8, dp=1.2, min_dist=25, param1=100, param2=25, min_radius=0, max_radius=0, max_out=64,
+                  return_info=False):
+    """cv2.HoughCircles(gray, HOUGH_GRADIENT, ...) (piece_detector.py:232-241) -> (n,3) f32 (x, y, r) or None;
+    with return_info also (support per circle, edge pixels, candidate centres)."""
+    g = _u8(gray_u8); H, W = g.shape
+    out = np.zeros((max_out, 4), np.float32); info = np.zeros(2, np.int32)
+    f = lib().orc_hough_circles; f.restype = C.c_int
+    n = f(_p(g), C.c_int(H), C.c_int(W), C.c_long(W), C.c_double(dp), C.c_double(min_dist), C.c_double(param1),
+          C.c_double(param2), C.c_int(min_radius), C.c_int(max_radius), _p(out), C.c_int(max_out), _p(info))
+    if n < 0:
+        raise ValueError("hough_circles: bad arguments")
+    n = min(n, max_out)
+    circles = out[:n, :3].copy() if n else None
+    if return_info:
+        return circles, out[:n, 3].astype(np.int32), int(info[0]), int(info[1])
+    return circles
+
+
 def refine_grid(bgr, return_edges=False):
     """SmartGridExtractor.refine_grid (grid_extractor.py:66-121) -> (grid_x, grid_y) lists of 9 ints."""
     bgr = _u8(bgr); H, W, _ = bgr.shape

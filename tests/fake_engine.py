@@ -5,7 +5,7 @@ import numpy as np
 
 import oracle as O
 from chessboard_vision_b200 import _lib
-from chessboard_vision_b200.engine import STATS_DTYPE
+from chessboard_vision_b200.engine import STATS_DTYPE, HOUGH_DTYPE, Engine
 from chessboard_vision_b200._lib import SquareParams, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE
 
 
@@ -146,3 +146,43 @@ class FakeEngine:
                                                   m2.ctypes.data_as(O.oracle.C.c_void_p), v2.ctypes.data_as(O.oracle.C.c_void_p))
                             M[...] = m2; V[...] = v2
         return out if want_stats else None
+
+    # -- Hough circles per square: geometry from the library's host code, circles from the oracle --
+    @property
+    def lib(self):
+        return _lib.load()
+
+    hough_params = Engine.hough_params
+    hough_geometry = Engine.hough_geometry
+    hough_circles = staticmethod(Engine.hough_circles)
+
+    def hough(self, planes, rects, params=None, select=None):
+        FakeEngine.launches += 1
+        params = params or self.hough_params()
+        pl = np.asarray(planes)
+        if pl.ndim == 2:
+            pl = pl[None]
+        geo = self.hough_geometry(rects, params)
+        sel = None if select is None else np.broadcast_to(np.asarray(select, np.uint8).reshape(-1, len(rects)), (pl.shape[0], len(rects)))
+        out = np.zeros((pl.shape[0], len(rects)), HOUGH_DTYPE)
+        for f in range(pl.shape[0]):
+            for i, (x, y, w, h) in enumerate(rects):
+                if w > _lib.HOUGH_MAX_DIM or h > _lib.HOUGH_MAX_DIM:
+                    raise ValueError("square larger than %d" % _lib.HOUGH_MAX_DIM)
+                if sel is not None and not sel[f, i]:
+                    out[f, i]["status"] = _lib.HOUGH_SKIPPED
+                    continue
+                c, sup, ne, nc = O.hough_circles(np.ascontiguousarray(pl[f, y:y + h, x:x + w]), dp=max(1.0, params.dp),
+                                                 min_dist=float(geo[i]["min_dist"]), param1=params.param1, param2=params.param2,
+                                                 min_radius=int(geo[i]["min_radius"]), max_radius=int(geo[i]["max_radius"]),
+                                                 max_out=4096, return_info=True)
+                k = 0 if c is None else len(c)
+                out[f, i]["count"], out[f, i]["n_edges"], out[f, i]["n_centers"] = k, ne, nc
+                k = min(k, _lib.HOUGH_MAX_CIRCLES)
+                if k:
+                    out[f, i]["xyr"][:k] = c[:k]
+                    out[f, i]["support"][:k] = sup[:k]
+        return out
+
+    def hough_state(self, state, rects, params=None, stream0=0, n=1, select=None):
+        return self.hough(state.planes[_lib.PLANE_PD_CUR][stream0:stream0 + n], rects, params, select)

@@ -138,6 +138,37 @@ def test_piece_detector_class(mods):
     assert vis2 <= vis
 
 
+def test_piece_detector_circles_match_reference(mods):
+    """_detect_circle_unified / calibrate_reference / detect_all_pieces with the Hough kernel against
+    the unmodified reference (cv2.HoughCircles) on the 64 squares of three boards."""
+    ref = json.load(open(os.path.join(G, "hough_reference.json")))
+    found = 0
+    for seed, rows in ref.items():
+        _, board = synth.board_with_pieces(int(seed), 7, 620)
+        det = mods["piece_detector"].PieceDetector()
+        squares = mods["grid_extractor"].GridExtractor().split_board(board)
+        for pos, sq in squares.items():
+            want = rows["%d_%d" % pos]
+            f, center, radius, kind = det._detect_circle_unified(det._preprocess_square(sq))
+            assert bool(f) == want["found"], (seed, pos)
+            if f:
+                assert list(center) == want["center"] and radius == want["radius"] and kind == want["kind"]
+                found += 1
+            full = det.detect_piece(sq, pos)
+            assert full["has_piece"] == want["has_piece"] and full["method"] == want["method"]
+            assert full["confidence"] == want["confidence"]
+        det.calibrate_reference(squares)
+        res, _ = mods["piece_detector"].PieceDetector().detect_all_pieces(squares, use_smoothing=False)
+        for pos in squares:
+            want = rows["%d_%d" % pos]
+            for got in (det.cached_results[pos], res[pos]):
+                assert got["has_piece"] == want["has_piece"] and got["method"] == want["method"], (seed, pos)
+                assert got["confidence"] == want["confidence"]
+                if want["method"] in ("hough", "tower_top"):
+                    assert list(got["center"]) == want["center"] and got["radius"] == want["radius"]
+    assert found >= 20
+
+
 def test_ragged_and_empty_square_dicts(mods, oracle):
     """Squares of different sizes that are not views of one board (atlas path), empty dicts, a missing key."""
     rng = np.random.default_rng(5)

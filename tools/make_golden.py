@@ -209,6 +209,49 @@ def main():
     rg["canny_97x133_30_100"] = sha(cv2.Canny(cv2.cvtColor(small, cv2.COLOR_BGR2GRAY), 30, 100))
     json.dump(rg, open(os.path.join(OUT, "refine_grid.json"), "w"), indent=1)
 
+    # ---- 9. Hough circles per square ("next" scope row, piece_detector.py:210-270) ----------------
+    cv2.setNumThreads(1)      # cv2.HoughCircles' multi-threaded merge order is not needed for the result, but keep it fixed
+    plane, hrects = synth.shape_atlas(3, 20, 8, 100, 512)
+    cases = [{"params": dict(dp=1.2, param1=100, param2=25, min_radius_ratio=0.20, max_radius_ratio=0.55, min_dist_div=3)},
+             {"params": dict(dp=1.2, param1=100, param2=30, min_radius_ratio=0.12, max_radius_ratio=0.55, min_dist_div=3)},
+             {"params": dict(dp=1.0, param1=50, param2=10, min_radius=0, max_radius=0, min_dist=5.5)},
+             {"params": dict(dp=2.0, param1=30, param2=5, min_radius=3, max_radius=2, min_dist=4.0)},
+             {"params": dict(dp=1.7, param1=3, param2=2, min_radius=2, max_radius=40, min_dist=12.0)}]
+    hz = {"plane": plane}
+    for ci, case in enumerate(cases):
+        q = case["params"]
+        for i, (x, y, w, h) in enumerate(hrects):
+            g = np.ascontiguousarray(plane[y:y + h, x:x + w])
+            md = min(h, w)
+            if "min_dist_div" in q:        # the reference's own argument expressions (piece_detector.py:225-241)
+                args = dict(minDist=md // q["min_dist_div"], minRadius=int(md * q["min_radius_ratio"]),
+                            maxRadius=int(md * q["max_radius_ratio"]))
+            else:
+                args = dict(minDist=q["min_dist"], minRadius=q["min_radius"], maxRadius=q["max_radius"])
+            if args["minDist"] <= 0:
+                hz["c%d_s%d" % (ci, i)] = np.zeros((0, 3), np.float32)
+                continue
+            c = cv2.HoughCircles(g, cv2.HOUGH_GRADIENT, dp=q["dp"], param1=q["param1"], param2=q["param2"], **args)
+            hz["c%d_s%d" % (ci, i)] = np.zeros((0, 3), np.float32) if c is None else c[0].astype(np.float32)
+    hz["meta"] = np.frombuffer(json.dumps({"rects": [list(r) for r in hrects], "cases": cases}).encode(), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "hough.npz"), **hz)
+    # the reference's own method on the 64 preprocessed squares of boards with pieces
+    hr = {}
+    for seed in (11, 12, 13):
+        _, bp = synth.board_with_pieces(seed, 7, 620)
+        det = pdm.PieceDetector()
+        rows = {}
+        for pos, sq in ge.GridExtractor().split_board(bp).items():
+            found, center, radius, kind = det._detect_circle_unified(det._preprocess_square(sq))
+            full = det.detect_piece(sq, pos)
+            rows["%d_%d" % pos] = {"found": bool(found), "center": None if center is None else [int(center[0]), int(center[1])],
+                                   "radius": None if radius is None else int(radius), "kind": kind,
+                                   "has_piece": bool(full["has_piece"]), "method": full["method"],
+                                   "confidence": float(full["confidence"])}
+        hr[str(seed)] = rows
+    json.dump(hr, open(os.path.join(OUT, "hough_reference.json"), "w"), indent=0)
+    cv2.setNumThreads(-1)
+
     # ---- 6. warp on a small frame (full output) ---------------------------------------------------
     img = synth.noise_frame(270, 480, 9)
     pts = synth.calib_points(270, 480)
