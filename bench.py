@@ -396,6 +396,40 @@ def main():
         extras["config3_change_stats_64_pairs"] = {"ms_per_batch": ms3, "frames_per_s": nb / ms3 * 1e3,
                                                    "what": "warp + 64 squares: absdiff delta, moments, centre/border, rings, "
                                                            "z-score detect + EMA update (resident inputs)"}
+        # "next" row: Hough circles on the 64 gray+blur squares of warped boards with pieces (k_hough),
+        # beside the reference's cv2.HoughCircles loop on this box's host cores
+        nh = 64
+        pboards = np.stack([synth.board_with_pieces(30 + i, 7, S)[1] for i in range(8)])
+        sth = eng.new_state(nh, S, S)
+        eng.squares(np.stack([pboards[i % 8] for i in range(nh)]), rects, eng.square_params(ops=SQ_PD_STATS), sth,
+                    want_stats=False)
+        hp = eng.hough_params()
+        hres = eng.hough_state(sth, rects, hp, 0, nh)
+        eng.profile(True)
+        for _ in range(5):
+            eng.hough_state(sth, rects, hp, 0, nh)
+        hprof = eng.profile_read()
+        eng.profile(False)
+        ms_h = hprof["k_hough"][0] / hprof["k_hough"][1]
+        cpu_h = None
+        try:
+            from oracle import ref_cv2
+            planes_h = [sth.get(i, 3) for i in range(2)]
+            t0 = time.perf_counter()
+            n_found = 0
+            for pl in planes_h:
+                for (x, y, w, h) in rects:
+                    n_found += ref_cv2.detect_circle_unified(np.ascontiguousarray(pl[y:y + h, x:x + w]))[0][0]
+            cpu_h = (time.perf_counter() - t0) * 1e3 / len(planes_h)
+        except ImportError:
+            pass
+        extras["next_hough_circles_64_squares"] = {
+            "device_ms_per_batch": ms_h, "frames": nh, "us_per_frame": ms_h / nh * 1e3,
+            "circles_per_frame": float(hres["count"].sum()) / nh, "edge_pixels_per_square": float(hres["n_edges"].mean()),
+            "cpu_reference_ms_per_frame": cpu_h,
+            "what": "cv2.HoughCircles(dp 1.2, 100/25, radii 20-55 %) on 64 squares per frame, one CTA per square; "
+                    "CPU: the reference's loop over 64 squares with cv2 (its default threads), 2 frames"}
+        sth.free()
         for x in (one, s1, o1, boards_in, warped, s3):
             x.free()
         st1.free(); st3.free()

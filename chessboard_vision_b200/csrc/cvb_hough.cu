@@ -30,7 +30,8 @@ constexpr int HW_ = HNT / 32;        // warps
 
 struct HoughLayout {                 // byte offsets into dynamic shared memory (sized for the largest square of the call)
     int off_acc, off_nz, off_bins, off_union, total;
-    int bins_pitch;                  // ints per warp
+    int bins_pitch;                  // ints per warp: the bins, then one mask bit per bin
+    int bins_words_at;               // where the mask words start inside a warp's slice
 };
 
 struct HoughMisc {
@@ -38,6 +39,10 @@ struct HoughMisc {
     unsigned long long best[HW_];
     float kx[CVB_HOUGH_MAX_CIRCLES], ky[CVB_HOUGH_MAX_CIRCLES];
 };
+
+// i / d for i * d < 2^32 with inv = floor((2^32 - 1) / d) + 1 (one IMAD.HI instead of a division)
+CVB_DEV int div_magic(int i, unsigned inv) { return inv ? (int)__umulhi((unsigned)i, inv) : i; }
+CVB_DEV unsigned magic_of(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
 
 CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
 {
@@ -48,7 +53,7 @@ CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
     gy = (q + 2 * r + s) - (a + 2 * b + c);
 }
 
-__global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
+__global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
                                               const cvb_hough_square *__restrict__ squares, int n_sq,
                                               const uint8_t *__restrict__ select, float dp, float idp, int canny_low,
                                               int canny_high, int acc_thr, HoughLayout L,
@@ -67,11 +72,13 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
     const cvb_hough_square S = squares[sq];
     const int w = S.w, h = S.h, gp = w + 2, npad = (h + 2) * gp;
     const int arows = S.acc_rows, acols = S.acc_cols, astep = acols + 2, ncells = (arows + 2) * astep;
+    const unsigned inv_gp = magic_of(gp), inv_astep = magic_of(astep), inv_acols = magic_of(acols);
     const int min_r = S.min_radius, max_r = S.max_radius, nbins = S.n_bins;
 
     int32_t *acc = reinterpret_cast<int32_t *>(smem + L.off_acc);
     uint16_t *nz = reinterpret_cast<uint16_t *>(smem + L.off_nz);
     int *bins = reinterpret_cast<int *>(smem + L.off_bins) + warp * L.bins_pitch;
+    unsigned *bmask = reinterpret_cast<unsigned *>(bins + L.bins_words_at);     // one bit per bin, after the bins
     // early view of the union: gray (u8) | mag (u16) | map (u8)
     uint8_t *s_g = smem + L.off_union;
     uint16_t *s_m = reinterpret_cast<uint16_t *>(smem + L.off_union + ((npad + 3) & ~3));
@@ -87,13 +94,13 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
     // ---- A: gray with a replicated border, magnitudes with a zero border ----
     const uint8_t *img = planes + (size_t)frame * plane_stride + (size_t)S.y * PW + S.x;
     for (int i = tid; i < npad; i += HNT) {
-        const int ly = i / gp, lx = i - ly * gp;
+        const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
         const int y = min(max(ly - 1, 0), h - 1), x = min(max(lx - 1, 0), w - 1);
         s_g[i] = __ldg(img + (size_t)y * PW + x);
     }
     __syncthreads();
     for (int i = tid; i < npad; i += HNT) {
-        const int ly = i / gp, lx = i - ly * gp;
+        const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
         int m = 0;
         if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
             int gx, gy;
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
     __syncthreads();
     // non-maximum suppression; map: 0 weak candidate, 1 no edge, 2 edge
     for (int i = tid; i < npad; i += HNT) {
-        const int ly = i / gp, lx = i - ly * gp;
+        const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
         uint8_t v = 1;
         if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
             const int m = s_m[i];
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
         bool take = false;
         int ly = 0, lx = 0;
         if (i < npad && s_map[i] == 2) {
-            ly = i / gp; lx = i - ly * gp;
+            ly = div_magic(i, inv_gp); lx = i - ly * gp;
             int gx, gy;
             sobel_at(s_g, gp, ly - 1, lx - 1, gx, gy);
             take = (gx | gy) != 0;
@@ -158,17 +165,39 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
     }
     __syncthreads();
     const int nnz = M.nnz;
+    // The unit steps (sx, sy) of a pixel's two rays are computed once, by one thread per edge pixel, into the
+    // (dead) magnitude array when the list fits there; a square with more edge pixels recomputes them per ray.
+    const bool dir_stored = nnz <= npad / 2;
+    int *s_dir = reinterpret_cast<int *>(s_m);
+    auto ray_step = [&](int x, int y, int &sx, int &sy) {
+        int gx, gy;
+        sobel_at(s_g, gp, y, x, gx, gy);
+        const float vx = (float)gx, vy = (float)gy;
+        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+        sx = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vx, idp), 1024.f), mag));
+        sy = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vy, idp), 1024.f), mag));
+    };
+    if (dir_stored) {
+        for (int e = tid; e < nnz; e += HNT) {
+            const int p = nz[e];
+            int sx, sy;
+            ray_step(p & 255, p >> 8, sx, sy);
+            s_dir[e] = (sx & 0xffff) | (sy << 16);
+        }
+        __syncthreads();
+    }
     {
         const int span = max_r - min_r + 1;
         // one warp per ray (pixel, direction): lanes take the radius steps
         for (int ray = warp; ray < 2 * nnz; ray += HW_) {
             const int p = nz[ray >> 1], x = p & 255, y = p >> 8;
-            int gx, gy;
-            sobel_at(s_g, gp, y, x, gx, gy);
-            const float vx = (float)gx, vy = (float)gy;
-            const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
-            int sx = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vx, idp), 1024.f), mag));
-            int sy = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(vy, idp), 1024.f), mag));
+            int sx, sy;
+            if (dir_stored) {
+                const int d = s_dir[ray >> 1];
+                sx = (int)(short)(d & 0xffff); sy = d >> 16;
+            } else {
+                ray_step(x, y, sx, sy);
+            }
             if (ray & 1) { sx = -sx; sy = -sy; }
             const int x0 = __float2int_rn(__fmul_rn(__fmul_rn((float)x, idp), 1024.f));
             const int y0 = __float2int_rn(__fmul_rn(__fmul_rn((float)y, idp), 1024.f));
@@ -189,7 +218,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
             bool take = false;
             int cell = 0;
             if (i < cw * ch) {
-                const int ay = i / cw + 1, ax = i - (ay - 1) * cw + 1;
+                const int ay = div_magic(i, inv_acols) + 1, ax = i - (ay - 1) * cw + 1;
                 cell = ay * astep + ax;
                 const int v = acc[cell];
                 take = v > acc_thr && v > acc[cell - 1] && v >= acc[cell + 1] && v > acc[cell - astep] && v >= acc[cell + astep];
@@ -207,7 +236,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
     const float dr = dp, fmin_r = (float)min_r;
     const float minr2 = __fmul_rn(fmin_r, fmin_r), maxr2 = __fmul_rn((float)max_r, (float)max_r);
     for (int c = warp; c < ncent; c += HW_) {
-        const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+        const int cell = c_idx[c], ay = div_magic(cell, inv_astep), ax = cell - ay * astep;
         const float cx = __fmul_rn((float)ax + 0.5f, dr), cy = __fmul_rn((float)ay + 0.5f, dr);
         for (int i = lane; i < nbins; i += 32) bins[i] = 0;
         __syncwarp();
@@ -221,20 +250,34 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
             }
         }
         __syncwarp();
+        // hough.cpp scans the bins downwards: the next non-empty bin j > 0 opens a window of 10 bins below it, then
+        // the scan resumes 11 bins lower.  A bit mask of the non-empty bins finds the window tops without the walk.
+        for (int c0 = 0; c0 < nbins; c0 += 32) {
+            const unsigned m = __ballot_sync(0xffffffffu, c0 + lane < nbins && bins[c0 + lane] != 0);
+            if (lane == 0) bmask[c0 >> 5] = m;
+        }
+        __syncwarp();
         if (lane == 0) {
             int max_count = 0;
             float rbest = 0.f;
-            for (int j = nbins - 1; j > 0; j--) {
-                if (bins[j]) {
-                    const int up = j;
-                    int cur = 0;
-                    for (; j > up - 10 && j >= 0; j--) cur += bins[j];
-                    const float rcur = __fadd_rn(__fmul_rn(__fdiv_rn(__fdiv_rn((float)(up + j), 2.f), 10.f), dr), fmin_r);
-                    if (__fmul_rn((float)cur, rbest) >= __fmul_rn((float)max_count, rcur) ||
-                        (rbest < 1.1920929e-07f && cur >= max_count)) {
-                        rbest = rcur; max_count = cur;
-                    }
+            int j = nbins - 1;
+            while (j > 0) {
+                int wd = j >> 5;
+                unsigned m = bmask[wd] & (0xffffffffu >> (31 - (j & 31)));
+                while (!m && wd > 0) m = bmask[--wd];
+                if (!m) break;
+                const int up = wd * 32 + 31 - __clz(m);
+                if (up <= 0) break;
+                int cur = 0;
+                const int lo = max(up - 9, 0);
+                for (int b = up; b >= lo; --b) cur += bins[b];
+                j = max(up - 10, -1);
+                const float rcur = __fadd_rn(__fmul_rn(__fdiv_rn(__fdiv_rn((float)(up + j), 2.f), 10.f), dr), fmin_r);
+                if (__fmul_rn((float)cur, rbest) >= __fmul_rn((float)max_count, rcur) ||
+                    (rbest < 1.1920929e-07f && cur >= max_count)) {
+                    rbest = rcur; max_count = cur;
                 }
+                j--;
             }
             c_r[c] = rbest;
             c_sup[c] = (uint16_t)(max_count > acc_thr ? max_count : 0);
@@ -249,7 +292,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
         for (int c = tid; c < ncent; c += HNT) {
             const unsigned sup = c_sup[c];
             if (sup) {
-                const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+                const int cell = c_idx[c], ay = div_magic(cell, inv_astep), ax = cell - ay * astep;
                 const unsigned long long key = ((unsigned long long)sup << 48) | ((unsigned long long)__float_as_uint(c_r[c]) << 16) |
                                                ((unsigned long long)(255 - ax) << 8) | (unsigned long long)(255 - ay);
                 best = key > best ? key : best;
@@ -277,7 +320,7 @@ __global__ void __launch_bounds__(HNT) k_hough(const uint8_t *__restrict__ plane
         }
         for (int c = tid; c < ncent; c += HNT) {
             if (c_sup[c]) {
-                const int cell = c_idx[c], ay = cell / astep, ax = cell - ay * astep;
+                const int cell = c_idx[c], ay = div_magic(cell, inv_astep), ax = cell - ay * astep;
                 const float ex = __fsub_rn(kx, __fmul_rn((float)ax + 0.5f, dr)), ey = __fsub_rn(ky, __fmul_rn((float)ay + 0.5f, dr));
                 if (__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < md2) c_sup[c] = 0;
             }
@@ -339,7 +382,8 @@ int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_strid
     L.off_acc = 0;
     L.off_nz = (int)up16(acc_b);
     L.off_bins = L.off_nz + (int)up16(nz_b);
-    L.bins_pitch = (int)((bins_i + 3) & ~(size_t)3);
+    L.bins_words_at = (int)((bins_i + 3) & ~(size_t)3);
+    L.bins_pitch = L.bins_words_at + (int)((((bins_i + 31) >> 5) + 3) & ~(size_t)3);
     L.off_union = L.off_bins + (int)up16((size_t)L.bins_pitch * 4 * HW_);
     L.total = L.off_union + (int)up16(uni_b);
     CVB_REQUIRE(L.total <= 220 * 1024, "Hough workspace of %d bytes per square exceeds shared memory", L.total);

@@ -105,6 +105,25 @@ def pd_statistics(gray, ref=None):
     return out
 
 
+def detect_circle_unified(gray, min_radius_ratio=0.20, max_radius_ratio=0.55, param1=100, param2=25):
+    """PieceDetector._detect_circle_unified (piece_detector.py:210-270): the cv2.HoughCircles call and
+    the choice of the circle nearest the square centre -> (found, centre, radius, kind), circles."""
+    h, w = gray.shape
+    md = min(h, w)
+    circles = cv2.HoughCircles(gray, cv2.HOUGH_GRADIENT, dp=1.2, minDist=md // 3, param1=param1, param2=param2,
+                               minRadius=int(md * min_radius_ratio), maxRadius=int(md * max_radius_ratio))
+    if circles is not None and len(circles[0]) > 0:
+        best, best_d = None, float("inf")
+        for c in circles[0]:
+            d = np.sqrt((c[0] - w // 2) ** 2 + (c[1] - h // 2) ** 2)
+            if d < md * 0.3 and d < best_d:
+                best, best_d = c, d
+        if best is not None:
+            r = int(best[2])
+            return (True, (int(best[0]), int(best[1])), r, "tower_top" if r < md * 0.20 else "hough"), circles
+    return (False, None, None, None), circles
+
+
 def cd_detect(gray_u8, mean, var, z_threshold=2.5):
     """change_detector.py:121-137,159 -> (changed_pixels, pct_changed, z_max)."""
     g = gray_u8.astype(np.float32)

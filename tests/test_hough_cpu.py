@@ -124,3 +124,24 @@ def test_dropin_circle_path_matches_reference(monkeypatch):
         for pos in squares:
             assert res[pos]["method"] == rows["%d_%d" % pos]["method"]
     assert found >= 20
+
+
+def test_ref_cv2_sequence_and_oracle_agree_with_reference_results():
+    """oracle/ref_cv2.detect_circle_unified (the CPU arm bench.py times) reproduces the reference's answers."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import ref_cv2
+    ref = json.load(open(os.path.join(GOLD, "hough_reference.json")))
+    rows = ref["11"]
+    _, board = synth.board_with_pieces(11, 7, 620)
+    for r in range(8):
+        for c in range(8):
+            sq = board[r * 77:(r + 1) * 77, c * 77:(c + 1) * 77]
+            g = O.square_preprocess(sq, 5)
+            (found, center, radius, kind), circles = ref_cv2.detect_circle_unified(g)
+            want = rows["%d_%d" % (c, 7 - r)]
+            assert found == want["found"] and kind == want["kind"]
+            mine = O.hough_circles(g, min_dist=25, min_radius=15, max_radius=42)
+            if circles is None:
+                assert mine is None
+            else:
+                assert np.array_equal(circles[0], mine)
