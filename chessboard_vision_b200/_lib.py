@@ -53,7 +53,7 @@ class SquareParams(C.Structure):
 
 class PipelineParams(C.Structure):
     _fields_ = [("enhance", EnhanceParams), ("squares", SquareParams),
-                ("warp_enhanced", C.c_int), ("board_size", C.c_int)]
+                ("warp_enhanced", C.c_int), ("board_size", C.c_int), ("rotate_180", C.c_int), ("reserved", C.c_int)]
 
 
 HOUGH_MAX_CIRCLES, HOUGH_MAX_DIM = 16, 128
@@ -127,6 +127,8 @@ SYMBOLS = [
     ("cvb_enhance", _I, [_P, _P, _I, _I, _I, C.POINTER(EnhanceParams), _P, _P, _P, _P]),
     ("cvb_get_perspective_transform", _I, [_P, _P, _P]),
     ("cvb_warp_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
+    ("cvb_warp_rot180_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
+    ("cvb_rotate_dev", _I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     ("cvb_canny_dev", _I, [_P, _P, _I, _I, _I, _D, _D, _P]),
     ("cvb_projections_dev", _I, [_P, _P, _I, _I, _I, _P, _P]),
     ("cvb_state_create", _I, [_P, _I, _I, _I, C.POINTER(_P)]),

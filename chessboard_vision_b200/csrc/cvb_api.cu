@@ -277,7 +277,7 @@ void cvb_pipeline_params_default(cvb_pipeline_params *p)
 {
     cvb_enhance_params_default(&p->enhance);
     cvb_square_params_default(&p->squares);
-    p->warp_enhanced = 1; p->board_size = 620;
+    p->warp_enhanced = 1; p->board_size = 620; p->rotate_180 = 0; p->reserved = 0;
 }
 
 int cvb_get_tables(uint16_t *gamma256, uint16_t *cbrt2048, int32_t *lab2yf512, uint8_t *invgamma4096, uint8_t *ltab2048)
@@ -528,7 +528,26 @@ int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const d
     CVB_REQUIRE(out_h >= 1 && out_w >= 1 && out_h <= 32768 && out_w <= 32768, "bad output size");
     double *d_m = nullptr;
     CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
-    return launch_warp(h, bgr, n, H, W, d_m, n_mats, out_h, out_w, warped);
+    return launch_warp(h, bgr, n, H, W, d_m, n_mats, out_h, out_w, 0, warped);
+}
+int cvb_warp_rot180_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *M9, int n_mats, int out_h,
+                        int out_w, uint8_t *warped)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && warped && M9, "null pointer");
+    CVB_REQUIRE(n_mats == 1 || n_mats == n, "n_mats must be 1 or n");
+    CVB_REQUIRE(out_h >= 1 && out_w >= 1 && out_h <= 32768 && out_w <= 32768, "bad output size");
+    double *d_m = nullptr;
+    CVB_TRY(upload_inverse_mats(h, M9, n_mats, &d_m));
+    return launch_warp(h, bgr, n, H, W, d_m, n_mats, out_h, out_w, 1, warped);
+}
+int cvb_rotate_dev(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C, int rotate_code, uint8_t *dst)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(src && dst && src != dst, "null pointer / in-place rotation");
+    CVB_REQUIRE(C == 1 || C == 3, "rotate: 1 or 3 channels, got %d", C);
+    CVB_REQUIRE(rotate_code >= 0 && rotate_code <= 2, "rotate code must be 0 (90 cw), 1 (180) or 2 (90 ccw)");
+    return launch_rotate(h, src, n, H, W, C, rotate_code, dst);
 }
 
 int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh,
@@ -805,7 +824,7 @@ static int pipeline_launch(cvb_handle *h, const uint8_t *bgr, int n, int H, int 
     if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
     if (!warped) CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * n, (void **)&warped));
     CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
-    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_minv, n_mats, S, S, warped));
+    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_minv, n_mats, S, S, p->rotate_180 != 0, warped));
     return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
 }
 

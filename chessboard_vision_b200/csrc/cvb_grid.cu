@@ -18,7 +18,7 @@ static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the 
 // One thread per destination pixel.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, int H, int W,
-                                              const double *__restrict__ minv, int n_mats, int OH, int OW,
+                                              const double *__restrict__ minv, int n_mats, int OH, int OW, int rot180,
                                               uint8_t *__restrict__ dst)
 {
     const int frame = blockIdx.z;
@@ -53,17 +53,62 @@ __global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, i
         if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w10 * p[0]; acc[1] += w10 * p[1]; acc[2] += w10 * p[2]; }
         if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w11 * p[0]; acc[1] += w11 * p[1]; acc[2] += w11 * p[2]; }
     }
-    uint8_t *o = dst + ((size_t)frame * OH * OW + (size_t)y * OW + x) * 3;
+    // cv2.rotate(warped, ROTATE_180) (game_session.py:125-126) is a permutation of the destination pixels
+    const int oy = rot180 ? OH - 1 - y : y, ox = rot180 ? OW - 1 - x : x;
+    uint8_t *o = dst + ((size_t)frame * OH * OW + (size_t)oy * OW + ox) * 3;
     o[0] = (uint8_t)((acc[0] + 512) >> 10);
     o[1] = (uint8_t)((acc[1] + 512) >> 10);
     o[2] = (uint8_t)((acc[2] + 512) >> 10);
 }
 int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats, int out_h,
-                int out_w, uint8_t *warped)
+                int out_w, int rot180, uint8_t *warped)
 {
     dim3 grid((out_w + 63) / 64, (out_h + 3) / 4, n);
     PROF(h, "k_warp");
-    k_warp<<<grid, 256, 0, h->stream>>>(bgr, H, W, d_minv, n_mats, out_h, out_w, warped);
+    k_warp<<<grid, 256, 0, h->stream>>>(bgr, H, W, d_minv, n_mats, out_h, out_w, rot180, warped);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
+// cv2.rotate (ROTATE_90_CLOCKWISE 0, ROTATE_180 1, ROTATE_90_COUNTERCLOCKWISE 2) of n images with C-byte pixels:
+// 32x32-pixel tiles through shared memory so that both the reads and the writes walk rows.
+template <int C>
+__global__ void __launch_bounds__(256) k_rotate(const uint8_t *__restrict__ src, int H, int W, int code, uint8_t *__restrict__ dst)
+{
+    __shared__ uint8_t tile[32][32 * C + 4];
+    const int frame = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const uint8_t *img = src + (size_t)frame * H * W * C;
+    uint8_t *out = dst + (size_t)frame * H * W * C;
+    const int tw = min(32, W - x0), th = min(32, H - y0);
+    for (int i = threadIdx.x; i < th * tw * C; i += 256) {
+        const int r = i / (tw * C), b = i - r * (tw * C);
+        tile[r][b] = img[((size_t)(y0 + r) * W + x0) * C + b];
+    }
+    __syncthreads();
+    if (code == 1) {                       // dst(y, x) = src(H-1-y, W-1-x): tile rows written right to left
+        for (int i = threadIdx.x; i < th * tw * C; i += 256) {
+            const int r = i / (tw * C), b = i - r * (tw * C), px = b / C, ch = b - px * C;
+            // destination row H-1-(y0+r), destination pixels W-1-(x0+tw-1) ... ascending
+            out[((size_t)(H - 1 - y0 - r) * W + (W - x0 - tw) + px) * C + ch] = tile[r][(tw - 1 - px) * C + ch];
+        }
+    } else {                               // output is W rows of H pixels
+        for (int i = threadIdx.x; i < th * tw * C; i += 256) {
+            const int orow = i / (th * C), b = i - orow * (th * C), px = b / C, ch = b - px * C;
+            // clockwise: dst(x, H-1-y) = src(y, x); counter-clockwise: dst(W-1-x, y) = src(y, x)
+            if (code == 0)
+                out[((size_t)(x0 + orow) * H + (H - y0 - th) + px) * C + ch] = tile[th - 1 - px][orow * C + ch];
+            else
+                out[((size_t)(W - 1 - x0 - orow) * H + y0 + px) * C + ch] = tile[px][orow * C + ch];
+        }
+    }
+}
+
+int launch_rotate(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C, int code, uint8_t *dst)
+{
+    dim3 grid((W + 31) / 32, (H + 31) / 32, n);
+    PROF(h, "k_rotate");
+    if (C == 3) k_rotate<3><<<grid, 256, 0, h->stream>>>(src, H, W, code, dst);
+    else k_rotate<1><<<grid, 256, 0, h->stream>>>(src, H, W, code, dst);
     LAUNCH_CHECK(h);
     return CVB_OK;
 }

@@ -154,7 +154,8 @@ int launch_projections(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
 
 // ---- cvb_grid.cu ----------------------------------------------------------------------
 int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats,
-                int out_h, int out_w, uint8_t *warped);
+                int out_h, int out_w, int rot180, uint8_t *warped);
+int launch_rotate(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C, int code, uint8_t *dst);
 int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C,
                    const cvb_rect *d_rects, const int32_t *d_mask_ofs, const uint8_t *d_masks, int n_sq, int max_px,
                    const uint8_t *d_select, cvb_state *st, int stream0, const cvb_square_params &p,

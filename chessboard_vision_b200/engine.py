@@ -413,14 +413,33 @@ class Engine:
         check(self.lib.cvb_get_perspective_transform(s.ctypes.data, d.ctypes.data, M.ctypes.data))
         return M.reshape(3, 3)
 
-    def warp(self, img, M, size):
+    def warp(self, img, M, size, rotate_180=False):
+        """cv2.warpPerspective (board_detection.py:69); rotate_180 adds game_session.py's cv2.rotate(ROTATE_180)."""
         single, n, H, W = _as_batch(img, 3)
         M = np.ascontiguousarray(M, np.float64)
         n_mats = 1 if M.ndim == 2 else M.shape[0]
         ow, oh = (size, size) if np.isscalar(size) else size
         src, tmp = self._in(img)
         dst = self.empty((oh, ow, 3) if single else (n, oh, ow, 3))
-        check(self.lib.cvb_warp_dev(self.h, src.ptr, n, H, W, M.ctypes.data, n_mats, int(oh), int(ow), dst.ptr))
+        fn = self.lib.cvb_warp_rot180_dev if rotate_180 else self.lib.cvb_warp_dev
+        check(fn(self.h, src.ptr, n, H, W, M.ctypes.data, n_mats, int(oh), int(ow), dst.ptr))
+        return self._out(dst, tmp, [src] if tmp else [])
+
+    def rotate(self, img, code):
+        """cv2.rotate(img, code) for (H,W) / (H,W,3) / (n,H,W,3) u8; code 0: 90 cw, 1: 180, 2: 90 ccw."""
+        shape = tuple(img.shape)
+        if len(shape) == 2:
+            n, H, W, ch, lead = 1, shape[0], shape[1], 1, ()
+        elif len(shape) == 3 and shape[2] == 3:
+            n, H, W, ch, lead = 1, shape[0], shape[1], 3, ()
+        elif len(shape) == 4 and shape[3] == 3:
+            n, H, W, ch, lead = shape[0], shape[1], shape[2], 3, (shape[0],)
+        else:
+            raise ValueError("rotate: expected (H,W), (H,W,3) or (n,H,W,3), got %r" % (shape,))
+        oh, ow = (H, W) if int(code) == 1 else (W, H)
+        src, tmp = self._in(img)
+        dst = self.empty(lead + ((oh, ow, 3) if ch == 3 else (oh, ow)))
+        check(self.lib.cvb_rotate_dev(self.h, src.ptr, n, H, W, ch, int(code), dst.ptr))
         return self._out(dst, tmp, [src] if tmp else [])
 
     # -- Canny / grid refinement (calibration time) ----------------------------------------------
@@ -585,7 +604,7 @@ class Engine:
         return rec["xyr"][:k].reshape(1, k, 3).copy() if k else None
 
     # -- whole path ----------------------------------------------------------------------------------
-    def pipeline_params(self, enhance=None, squares=None, warp_enhanced=True, board_size=620):
+    def pipeline_params(self, enhance=None, squares=None, warp_enhanced=True, board_size=620, rotate_180=False):
         p = PipelineParams()
         self.lib.cvb_pipeline_params_default(C.byref(p))
         if enhance is not None:
@@ -593,6 +612,7 @@ class Engine:
         if squares is not None:
             p.squares = squares
         p.warp_enhanced = int(bool(warp_enhanced)); p.board_size = int(board_size)
+        p.rotate_180 = int(bool(rotate_180))
         return p
 
     def pipeline(self, frames, M, rects, params, state=None, stream0=0, select=None):

@@ -175,6 +175,16 @@ int cvb_get_perspective_transform(const float *src_xy4, const float *dst_xy4, do
 int cvb_warp_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                  const double *M9, int n_mats, int out_h, int out_w, uint8_t *warped);
 
+/* the same followed by cv2.rotate(warped, cv2.ROTATE_180) (game_session.py:103-104,
+ * 125-126: orientation_flipped), folded into the warp's stores              */
+int cvb_warp_rot180_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
+                        const double *M9, int n_mats, int out_h, int out_w, uint8_t *warped);
+/* cv2.rotate(img, code): 0 ROTATE_90_CLOCKWISE, 1 ROTATE_180,
+ * 2 ROTATE_90_COUNTERCLOCKWISE; n images of H x W x C (C = 1 or 3); the 90-degree
+ * codes write n images of W x H x C   (ui_renderer.py:148-149, game_session.py:126) */
+int cvb_rotate_dev(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C,
+                   int rotate_code, uint8_t *dst);
+
 /* ---- SmartGridExtractor.refine_grid building blocks (calibration time) -------- */
 /* cv2.Canny(gray, low, high) (aperture 3, L1 gradient)   grid_extractor.py:74 */
 int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W,
@@ -303,6 +313,9 @@ typedef struct {
     cvb_square_params  squares;
     int warp_enhanced;          /* 1: warp the enhanced frame, 0: the raw frame  */
     int board_size;             /* 620 = min(1280,720)-100  board_detection.py:65 */
+    int rotate_180;             /* 1: cv2.rotate(warped, ROTATE_180) before the split, as
+                                 * game_session.py:125-126 does when orientation_flipped  */
+    int reserved;
 } cvb_pipeline_params;
 void cvb_pipeline_params_default(cvb_pipeline_params *p);
 

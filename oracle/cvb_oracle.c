@@ -1054,6 +1054,23 @@ ORC_API int orc_hough_circles(const u8 *gray, int H, int W, long stride, double 
     return count;
 }
 
+/* cv2.rotate(img, code): 0 ROTATE_90_CLOCKWISE, 1 ROTATE_180, 2 ROTATE_90_COUNTERCLOCKWISE            */
+/* (game_session.py:103-104,125-126 rotate the warped board by 180 degrees when orientation_flipped).  */
+/* A pure permutation: clockwise dst(x, H-1-y) = src(y, x); 180 dst(H-1-y, W-1-x); ccw dst(W-1-x, y).  */
+ORC_API int orc_rotate(const u8 *src, int H, int W, int C, int code, u8 *dst)
+{
+    if (code < 0 || code > 2) return -1;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            long o;
+            if (code == 1) o = (long)(H - 1 - y) * W + (W - 1 - x);
+            else if (code == 0) o = (long)x * H + (H - 1 - y);
+            else o = (long)(W - 1 - x) * H + y;
+            for (int c = 0; c < C; c++) dst[o * C + c] = src[((long)y * W + x) * C + c];
+        }
+    return 0;
+}
+
 /* find_internal_lines (grid_extractor.py:83-110): border 0, seven window arg-max positions, border `length` */
 static void internal_lines(const uint64_t *proj, int length, int32_t *lines)
 {

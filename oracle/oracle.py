@@ -333,6 +333,17 @@ def canny(gray_u8, low=50, high=150):
     return out
 
 
+def rotate(img, code):
+    """cv2.rotate(img, code) (0: 90 degrees clockwise, 1: 180, 2: 90 counter-clockwise) for (H,W) / (H,W,C) u8."""
+    a = _u8(img); H, W = a.shape[:2]; ch = 1 if a.ndim == 2 else a.shape[2]
+    shape = (H, W) if code == 1 else (W, H)
+    out = np.empty(shape + (() if a.ndim == 2 else (ch,)), np.uint8)
+    f = lib().orc_rotate; f.restype = C.c_int
+    if f(_p(a), C.c_int(H), C.c_int(W), C.c_int(ch), C.c_int(int(code)), _p(out)) != 0:
+        raise ValueError("rotate: bad code %r" % (code,))
+    return out
+
+
 def hough_circles(gray_u8, dp=1.2, min_dist=25, param1=100, param2=25, min_radius=0, max_radius=0, max_out=64,
                   return_info=False):
     """cv2.HoughCircles(gray, HOUGH_GRADIENT, ...) (piece_detector.py:232-241) -> (n,3) f32 (x, y, r) or None;

@@ -252,6 +252,19 @@ def main():
     json.dump(hr, open(os.path.join(OUT, "hough_reference.json"), "w"), indent=0)
     cv2.setNumThreads(-1)
 
+    # ---- 10. cv2.rotate (game_session.py:103-104,125-126: the warped board turned by 180 degrees) ----
+    rot = {}
+    for name, im in (("noise_37x53x3", synth.noise_frame(37, 53, 5)), ("noise_64x96x3", synth.noise_frame(64, 96, 6)),
+                     ("gray_45x31", synth.noise_frame(45, 31, 7)[:, :, 0].copy())):
+        for code, cname in ((cv2.ROTATE_90_CLOCKWISE, "cw"), (cv2.ROTATE_180, "180"), (cv2.ROTATE_90_COUNTERCLOCKWISE, "ccw")):
+            rot["%s_%s" % (name, cname)] = {"code": int(code), "sha": sha(cv2.rotate(im, code)),
+                                            "shape": list(cv2.rotate(im, code).shape)}
+    # the reference's sequence: warp_image then rotate 180 (orientation_flipped)
+    img = synth.noise_frame(270, 480, 9)
+    w180 = cv2.rotate(bd.warp_image(img, synth.calib_points(270, 480), display_size=(200, 180), margin=20)[0], cv2.ROTATE_180)
+    rot["warp_small_rot180_sha"] = sha(w180)
+    json.dump(rot, open(os.path.join(OUT, "rotate.json"), "w"), indent=1)
+
     # ---- 6. warp on a small frame (full output) ---------------------------------------------------
     img = synth.noise_frame(270, 480, 9)
     pts = synth.calib_points(270, 480)
