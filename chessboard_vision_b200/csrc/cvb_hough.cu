@@ -28,16 +28,19 @@ namespace {
 constexpr int HNT = 256;             // threads per square
 constexpr int HW_ = HNT / 32;        // warps
 
-struct HoughLayout {                 // byte offsets into dynamic shared memory (sized for the largest square of the call)
-    int off_acc, off_nz, off_bins, off_union, total;
+// Byte offsets into dynamic shared memory, sized for the largest square of the call.  Two regions are reused:
+//   [off_acc]    the vote accumulator (phases B, C), then the per-warp radius histograms (phase D)
+//   [off_union]  gray | Canny map | ray steps (phases A, B), then the candidate list (phases C-E)
+struct HoughLayout {
+    int off_acc, off_nz, off_union, total;
     int bins_pitch;                  // ints per warp: the bins, then one mask bit per bin
     int bins_words_at;               // where the mask words start inside a warp's slice
+    int dir_cap;                     // ray-step entries that fit behind the early view of the union
 };
 
 struct HoughMisc {
     int nnz, ncent, kept, pad;
     unsigned long long best[HW_];
-    float kx[CVB_HOUGH_MAX_CIRCLES], ky[CVB_HOUGH_MAX_CIRCLES];
 };
 
 // i / d for i * d < 2^32 with inv = floor((2^32 - 1) / d) + 1 (one IMAD.HI instead of a division)
@@ -53,7 +56,7 @@ CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
     gy = (q + 2 * r + s) - (a + 2 * b + c);
 }
 
-__global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
+__global__ void __launch_bounds__(HNT, 4) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
                                               const cvb_hough_square *__restrict__ squares, int n_sq,
                                               const uint8_t *__restrict__ select, float dp, float idp, int canny_low,
                                               int canny_high, int acc_thr, HoughLayout L,
@@ -77,12 +80,13 @@ __global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ pl
 
     int32_t *acc = reinterpret_cast<int32_t *>(smem + L.off_acc);
     uint16_t *nz = reinterpret_cast<uint16_t *>(smem + L.off_nz);
-    int *bins = reinterpret_cast<int *>(smem + L.off_bins) + warp * L.bins_pitch;
+    int *bins = reinterpret_cast<int *>(smem + L.off_acc) + warp * L.bins_pitch;  // phase D only: the accumulator is dead then
     unsigned *bmask = reinterpret_cast<unsigned *>(bins + L.bins_words_at);     // one bit per bin, after the bins
-    // early view of the union: gray (u8) | mag (u16) | map (u8)
+    // early view of the union: gray (u8) | map (u8) | ray steps (2 x i16)
+    const int npad4 = (npad + 3) & ~3;
     uint8_t *s_g = smem + L.off_union;
-    uint16_t *s_m = reinterpret_cast<uint16_t *>(smem + L.off_union + ((npad + 3) & ~3));
-    uint8_t *s_map = smem + L.off_union + ((npad + 3) & ~3) + 2 * npad;
+    uint8_t *s_map = smem + L.off_union + npad4;
+    int *s_dir = reinterpret_cast<int *>(smem + L.off_union + 2 * npad4);
     // late view: centre cells (u16) | radius (f32) | support (u16)
     const int maxc = ncells / 2 + 1;
     float *c_r = reinterpret_cast<float *>(smem + L.off_union);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ pl
 
     if (tid == 0) { M.nnz = 0; M.ncent = 0; M.kept = 0; }
     for (int i = tid; i < ncells; i += HNT) acc[i] = 0;
-    // ---- A: gray with a replicated border, magnitudes with a zero border ----
+    // ---- A: gray with a replicated border; Canny ----
     const uint8_t *img = planes + (size_t)frame * plane_stride + (size_t)S.y * PW + S.x;
     for (int i = tid; i < npad; i += HNT) {
         const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
@@ -99,34 +103,32 @@ __global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ pl
         s_g[i] = __ldg(img + (size_t)y * PW + x);
     }
     __syncthreads();
-    for (int i = tid; i < npad; i += HNT) {
-        const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
-        int m = 0;
-        if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
-            int gx, gy;
-            sobel_at(s_g, gp, ly - 1, lx - 1, gx, gy);
-            m = abs(gx) + abs(gy);
-        }
-        s_m[i] = (uint16_t)m;
-    }
-    __syncthreads();
-    // non-maximum suppression; map: 0 weak candidate, 1 no edge, 2 edge
+    // L1 gradient magnitude of pixel (y, x); zero outside the image, as OpenCV's padded magnitude rows
+    auto mag_at = [&](int y, int x) {
+        if ((unsigned)y >= (unsigned)h || (unsigned)x >= (unsigned)w) return 0;
+        int gx, gy;
+        sobel_at(s_g, gp, y, x, gx, gy);
+        return abs(gx) + abs(gy);
+    };
+    // non-maximum suppression; map: 0 weak candidate, 1 no edge, 2 edge.  Few pixels pass the low threshold, so the
+    // two neighbour magnitudes along the gradient are recomputed there instead of keeping a magnitude array.
     for (int i = tid; i < npad; i += HNT) {
         const int ly = div_magic(i, inv_gp), lx = i - ly * gp;
         uint8_t v = 1;
         if (ly >= 1 && ly <= h && lx >= 1 && lx <= w) {
-            const int m = s_m[i];
+            const int y = ly - 1, x = lx - 1;
+            int xs, ys;
+            sobel_at(s_g, gp, y, x, xs, ys);
+            const int m = abs(xs) + abs(ys);
             if (m > canny_low) {
-                int xs, ys;
-                sobel_at(s_g, gp, ly - 1, lx - 1, xs, ys);
                 const int ax = abs(xs), ay = abs(ys) << 15;            // < 2^26
                 const int tg22x = ax * 13573, tg67x = tg22x + (ax << 16);   // < 2^27
                 bool cand;
-                if (ay < tg22x) cand = m > s_m[i - 1] && m >= s_m[i + 1];
-                else if (ay > tg67x) cand = m > s_m[i - gp] && m >= s_m[i + gp];
+                if (ay < tg22x) cand = m > mag_at(y, x - 1) && m >= mag_at(y, x + 1);
+                else if (ay > tg67x) cand = m > mag_at(y - 1, x) && m >= mag_at(y + 1, x);
                 else {
-                    const int s = (xs ^ ys) < 0 ? -1 : 1;
-                    cand = m > s_m[i - gp - s] && m > s_m[i + gp + s];
+                    const int sgn = (xs ^ ys) < 0 ? -1 : 1;
+                    cand = m > mag_at(y - 1, x - sgn) && m > mag_at(y + 1, x + sgn);
                 }
                 if (cand) v = m > canny_high ? 2 : 0;
             }
@@ -165,10 +167,9 @@ __global__ void __launch_bounds__(HNT, 3) k_hough(const uint8_t *__restrict__ pl
     }
     __syncthreads();
     const int nnz = M.nnz;
-    // The unit steps (sx, sy) of a pixel's two rays are computed once, by one thread per edge pixel, into the
-    // (dead) magnitude array when the list fits there; a square with more edge pixels recomputes them per ray.
-    const bool dir_stored = nnz <= npad / 2;
-    int *s_dir = reinterpret_cast<int *>(s_m);
+    // The unit steps (sx, sy) of a pixel's two rays are computed once, by one thread per edge pixel, when the
+    // list fits the buffer behind the Canny map; a square with more edge pixels recomputes them per ray.
+    const bool dir_stored = nnz <= L.dir_cap;
     auto ray_step = [&](int x, int y, int &sx, int &sy) {
         int gx, gy;
         sobel_at(s_g, gp, y, x, gx, gy);
@@ -367,24 +368,26 @@ int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_strid
     const int canny_high = (int)std::lrint(p.param1), acc_thr = (int)std::lrint(p.param2);
     const int canny_low = std::max(1, canny_high / 2);
     // shared-memory layout for the largest square of the list
-    size_t acc_b = 0, nz_b = 0, bins_i = 0, uni_b = 0;
+    size_t acc_b = 0, nz_b = 0, bins_i = 0, early_b = 0, late_b = 0;
     for (int i = 0; i < n_sq; ++i) {
         const cvb_hough_square &s = squares[i];
         const size_t npad = (size_t)(s.h + 2) * (s.w + 2), ncells = (size_t)(s.acc_rows + 2) * (s.acc_cols + 2);
         acc_b = std::max(acc_b, ncells * 4);
         nz_b = std::max(nz_b, (size_t)s.h * s.w * 2);
         bins_i = std::max(bins_i, (size_t)std::max(s.n_bins, 1));
-        const size_t early = ((npad + 3) & ~(size_t)3) + 3 * npad, late = 8 * (ncells / 2 + 1);
-        uni_b = std::max(uni_b, std::max(early, late));
+        early_b = std::max(early_b, 2 * ((npad + 3) & ~(size_t)3));
+        late_b = std::max(late_b, 8 * (ncells / 2 + 1));
     }
     auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     HoughLayout L;
-    L.off_acc = 0;
-    L.off_nz = (int)up16(acc_b);
-    L.off_bins = L.off_nz + (int)up16(nz_b);
     L.bins_words_at = (int)((bins_i + 3) & ~(size_t)3);
     L.bins_pitch = L.bins_words_at + (int)((((bins_i + 31) >> 5) + 3) & ~(size_t)3);
-    L.off_union = L.off_bins + (int)up16((size_t)L.bins_pitch * 4 * HW_);
+    L.off_acc = 0;
+    L.off_nz = (int)up16(std::max(acc_b, (size_t)L.bins_pitch * 4 * HW_));
+    L.off_union = L.off_nz + (int)up16(nz_b);
+    // ray steps behind the early view: what the candidate list leaves free, at least 512 entries
+    const size_t uni_b = std::max(late_b, early_b + 4 * 512);
+    L.dir_cap = (int)((uni_b - early_b) / 4);
     L.total = L.off_union + (int)up16(uni_b);
     CVB_REQUIRE(L.total <= 220 * 1024, "Hough workspace of %d bytes per square exceeds shared memory", L.total);
     const void *fn = (const void *)k_hough;
