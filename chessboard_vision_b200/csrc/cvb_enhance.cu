@@ -918,7 +918,41 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
     const int X = x0 - PADX + 4 * lane;            // first pixel of this lane's group
     const bool inside = X >= 0 && X + 3 < W;
     const bool interior_col = lane >= 1 && lane <= FW / 4 && X < W;
-    for (int ly = warp; ly < GH; ly += 8) {
+    // Tiles whose 40 staged rows all exist (no mirrored or missing rows): an aligned 4-pixel group advances by a
+    // constant number of words per staged row, so the five rows of a warp are loaded up front and every address
+    // is one pointer plus a compile-time multiple of the row stride.
+    const bool rows_inside = FAST && y0 >= R && y0 + FH + R <= H;          // uniform over the block
+    const bool fast_lane = rows_inside && inside;
+    if (fast_lane) {
+        const size_t row32 = (size_t)W * 3 / 4, grow32 = (size_t)W / 4;    // words per image row (W % 4 == 0)
+        const size_t p0 = (size_t)(y0 - R + warp) * W + X;
+        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(img + p0 * 3);
+        uint32_t *e32 = enhanced ? reinterpret_cast<uint32_t *>(enhanced + (fo + p0) * 3) : nullptr;
+        uint32_t *g32 = gray ? reinterpret_cast<uint32_t *>(gray + fo + p0) : nullptr;
+        uint32_t wv[5][3];
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            wv[it][0] = __ldg(p32 + it * 8 * row32); wv[it][1] = __ldg(p32 + it * 8 * row32 + 1);
+            wv[it][2] = __ldg(p32 + it * 8 * row32 + 2);
+        }
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const int ly = warp + 8 * it;
+            uint32_t w0 = wv[it][0], w1 = wv[it][1], w2 = wv[it][2];
+            if (NORM && !identity) {
+                w0 = s_map[w0 & 0xff] | (s_map[(w0 >> 8) & 0xff] << 8) | (s_map[(w0 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w0 >> 24] << 24);
+                w1 = s_map[w1 & 0xff] | (s_map[(w1 >> 8) & 0xff] << 8) | (s_map[(w1 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w1 >> 24] << 24);
+                w2 = s_map[w2 & 0xff] | (s_map[(w2 >> 8) & 0xff] << 8) | (s_map[(w2 >> 16) & 0xff] << 16) | ((uint32_t)s_map[w2 >> 24] << 24);
+            }
+            const uint32_t gpack = gray4_from_words(w0, w1, w2);
+            if (interior_col && ly >= R && ly < GH - R) {
+                if (enhanced) { e32[it * 8 * row32] = w0; e32[it * 8 * row32 + 1] = w1; e32[it * 8 * row32 + 2] = w2; }
+                if (gray) g32[it * 8 * grow32] = gpack;
+            }
+            *reinterpret_cast<uint32_t *>(&s_g[ly][4 * lane]) = gpack;
+        }
+    }
+    for (int ly = warp; ly < GH && !fast_lane; ly += 8) {
         const int Y = y0 - R + ly;
         const int sy = reflect101(Y, H);
         const uint8_t *rowp = img + (size_t)sy * W * 3;
@@ -1006,14 +1040,17 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
         const int x = 4 * lane, Xo = x0 + x;
         if (Xo < W) {
             const int nvalid = FAST ? 4 : min(4, W - Xo);
-            for (int ly = warp; ly < FH; ly += 8) {
-                const int Y = y0 + ly;
-                if (Y >= H) break;
-                const uint2 r0 = *reinterpret_cast<const uint2 *>(&s_h[ly][x]);
-                const uint2 r1 = *reinterpret_cast<const uint2 *>(&s_h[ly + 1][x]);
-                const uint2 r2 = *reinterpret_cast<const uint2 *>(&s_h[ly + 2][x]);
-                const uint2 r3 = *reinterpret_cast<const uint2 *>(&s_h[ly + 3][x]);
-                const uint2 r4 = *reinterpret_cast<const uint2 *>(&s_h[ly + 4][x]);
+            uint8_t *orow = blurred ? blurred + fo + (size_t)(y0 + warp) * W + Xo : nullptr;
+            const uint16_t *hrow = &s_h[warp][x];
+#pragma unroll
+            for (int it = 0; it < (FH + 7) / 8; ++it, hrow += 8 * FW, orow += (size_t)8 * W) {
+                const int ly = warp + 8 * it;
+                if (ly >= FH || y0 + ly >= H) break;
+                const uint2 r0 = *reinterpret_cast<const uint2 *>(hrow);
+                const uint2 r1 = *reinterpret_cast<const uint2 *>(hrow + FW);
+                const uint2 r2 = *reinterpret_cast<const uint2 *>(hrow + 2 * FW);
+                const uint2 r3 = *reinterpret_cast<const uint2 *>(hrow + 3 * FW);
+                const uint2 r4 = *reinterpret_cast<const uint2 *>(hrow + 4 * FW);
                 // two 16-bit lanes per word; each lane's sum is <= 255*256 = 65280, so no carry crosses lanes
                 const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
                 const uint32_t hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
@@ -1026,11 +1063,10 @@ __global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src,
                         if (j < nvalid) atomicAdd(&myh[ov[j]], 1);
                 }
                 if (blurred) {
-                    uint8_t *o = blurred + fo + (size_t)Y * W + Xo;
                     if (FAST)
-                        *reinterpret_cast<uint32_t *>(o) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
+                        *reinterpret_cast<uint32_t *>(orow) = (uint32_t)o0 | ((uint32_t)o1 << 8) | ((uint32_t)o2 << 16) | ((uint32_t)o3 << 24);
                     else
-                        for (int j = 0; j < nvalid; ++j) o[j] = (uint8_t)ov[j];
+                        for (int j = 0; j < nvalid; ++j) orow[j] = (uint8_t)ov[j];
                 }
             }
         }
