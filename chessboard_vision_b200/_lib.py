@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcvb200.so")
+LIB_PATH = os.environ.get("CVB200_LIB") or os.path.join(_HERE, "libcvb200.so")   # override: a differently built library
 
 
 class CvbError(RuntimeError):
