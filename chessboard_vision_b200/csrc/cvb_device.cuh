@@ -11,6 +11,9 @@ CVB_DEV int reflect101(int p, int n)
     while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
     return p;
 }
+// i / d for 0 <= i, i * d < 2^32, with inv = ceil(2^32 / d): one IMAD.HI instead of a division (inv == 0 means d == 1)
+CVB_DEV int div_magic(int i, unsigned inv) { return inv ? (int)__umulhi((unsigned)i, inv) : i; }
+CVB_DEV unsigned magic_of(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
 CVB_DEV int clamp_u8(int v) { return min(max(v, 0), 255); }
 // saturate_cast<uchar>(float): round half to even, then clamp
 CVB_DEV int round_u8(float v) { return clamp_u8(__float2int_rn(v)); }

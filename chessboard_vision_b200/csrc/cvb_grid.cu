@@ -159,30 +159,29 @@ CVB_DEV int reflect_near(int p, int n)
     return p >= n ? 2 * n - 2 - p : p;
 }
 
-// horizontal Q8 pass over the whole square (rows by warp, columns by lane: no divisions)
+// horizontal Q8 pass over the whole square; pixels are dealt to the threads in row-major order so that a
+// square of any width keeps all lanes busy
 template <int K>
-CVB_DEV void hpass(const uint8_t *s_g, uint16_t *s_h, const int *q, int k_rt, int w, int h, bool near_ok)
+CVB_DEV void hpass(const uint8_t *s_g, uint16_t *s_h, const int *q, int k_rt, int w, int h, unsigned inv_w, bool near_ok)
 {
-    const int k = K ? K : k_rt, r = k >> 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int y = warp; y < h; y += 8) {
+    const int k = K ? K : k_rt, r = k >> 1, n = w * h;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int y = div_magic(i, inv_w), x = i - y * w;
         const uint8_t *row = s_g + y * w;
-        for (int x = lane; x < w; x += 32) {
-            uint32_t s = 0;
-            if (K == 5) {
-                if (x >= 2 && x + 2 < w) {
-                    s = q[0] * row[x - 2] + q[1] * row[x - 1] + q[2] * row[x] + q[3] * row[x + 1] + q[4] * row[x + 2];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j)
-                        s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - 2, w) : reflect101(x + j - 2, w)];
-                }
+        uint32_t s = 0;
+        if (K == 5) {
+            if (x >= 2 && x + 2 < w) {
+                s = q[0] * row[x - 2] + q[1] * row[x - 1] + q[2] * row[x] + q[3] * row[x + 1] + q[4] * row[x + 2];
             } else {
-                for (int j = 0; j < k; ++j)
-                    s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - r, w) : reflect101(x + j - r, w)];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - 2, w) : reflect101(x + j - 2, w)];
             }
-            s_h[y * w + x] = (uint16_t)s;
+        } else {
+            for (int j = 0; j < k; ++j)
+                s += (uint32_t)q[j] * row[near_ok ? reflect_near(x + j - r, w) : reflect101(x + j - r, w)];
         }
+        s_h[i] = (uint16_t)s;
     }
 }
 template <int K>
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
     __shared__ unsigned long long s_acc[16];
     __shared__ unsigned s_cd_nan;
     __shared__ int s_cd_zbits;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int sq = blockIdx.x, frame = blockIdx.y;
     const cvb_rect rc = a.rects[sq];
     const int w = rc.w, h = rc.h, n = w * h;
@@ -227,24 +226,33 @@ __global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
 
     if (tid < 16) s_acc[tid] = 0ull;
     if (tid == 0) { s_cd_nan = 0; s_cd_zbits = __float_as_int(-INFINITY); }
-    for (int y = warp; y < h; y += 8) {
-        const uint8_t *rowp = board + ((size_t)(rc.y + y) * a.BW + rc.x) * a.C;
+    const unsigned inv_w = magic_of(w);
+    {
+        const uint8_t *org = board + ((size_t)rc.y * a.BW + rc.x) * a.C;
+        const int pitch = a.BW * a.C;
         if (a.C == 3) {
-            for (int xb = lane; xb < w; xb += 128) {
+            for (int i0 = tid; i0 < n; i0 += 256 * 4) {
                 int c0[4], c1[4], c2[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int x = xb + 32 * j;
-                    if (x < w) { c0[j] = __ldg(rowp + 3 * x); c1[j] = __ldg(rowp + 3 * x + 1); c2[j] = __ldg(rowp + 3 * x + 2); }
+                    const int i = i0 + 256 * j;
+                    if (i < n) {
+                        const int y = div_magic(i, inv_w), x = i - y * w;
+                        const uint8_t *p = org + (size_t)y * pitch + 3 * x;
+                        c0[j] = __ldg(p); c1[j] = __ldg(p + 1); c2[j] = __ldg(p + 2);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int x = xb + 32 * j;
-                    if (x < w) s_g[y * w + x] = (uint8_t)gray_px(c0[j], c1[j], c2[j]);
+                    const int i = i0 + 256 * j;
+                    if (i < n) s_g[i] = (uint8_t)gray_px(c0[j], c1[j], c2[j]);
                 }
             }
         } else {
-            for (int x = lane; x < w; x += 32) s_g[y * w + x] = __ldg(rowp + x);
+            for (int i = tid; i < n; i += 256) {
+                const int y = div_magic(i, inv_w), x = i - y * w;
+                s_g[i] = __ldg(org + (size_t)y * pitch + x);
+            }
         }
     }
     __syncthreads();
@@ -262,13 +270,16 @@ __global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
     const bool near_pd = w > (a.p.pd_blur >> 1) && h > (a.p.pd_blur >> 1);
     const bool near_cd = w > (a.p.cd_blur >> 1) && h > (a.p.cd_blur >> 1);
     if (pass1) {
-        if (a.p.pd_blur == 5) hpass<5>(s_g, s_h, a.pd_q, 5, w, h, near_pd);
-        else hpass<0>(s_g, s_h, a.pd_q, a.p.pd_blur, w, h, near_pd);
+        if (a.p.pd_blur == 5) hpass<5>(s_g, s_h, a.pd_q, 5, w, h, inv_w, near_pd);
+        else hpass<0>(s_g, s_h, a.pd_q, a.p.pd_blur, w, h, inv_w, near_pd);
     }
     __syncthreads();
 
-    uint8_t *const pd_ref = a.pd_ref, *const pd_cur = a.pd_cur, *const flags = a.flags;
-    float *const cd_mean = a.cd_mean, *const cd_var = a.cd_var;
+    // state planes of this stream slot, addressed from the square's first pixel with 32-bit offsets
+    const size_t org = so + (size_t)rc.y * a.BW + rc.x;
+    uint8_t *const pd_ref = a.pd_ref ? a.pd_ref + org : nullptr, *const pd_cur = a.pd_cur ? a.pd_cur + org : nullptr,
+                   *const flags = a.flags ? a.flags + org : nullptr;
+    float *const cd_mean = a.cd_mean ? a.cd_mean + org : nullptr, *const cd_var = a.cd_var ? a.cd_var + org : nullptr;
     const float zthr = a.p.z_threshold, alpha = a.p.alpha, oma = a.p.one_minus_alpha, minvar = a.p.min_variance,
                 initvar = a.p.initial_variance;
     unsigned sum = 0, sad = 0, csum = 0, ccnt = 0, bsum = 0, bcnt = 0;
@@ -279,23 +290,23 @@ __global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
     bool cd_nan = false;
     const uint8_t *mask = a.masks + a.mask_ofs[sq];
 
-    // Per row, a lane owns columns lane, lane+32, ... in batches of U: all state loads of a batch are issued
-    // before any arithmetic or store, so several memory round trips overlap (the loop is latency bound).
+    // Pixels are dealt to the threads in row-major order, U per thread and round: all state loads of a batch
+    // are issued before any arithmetic or store, so several memory round trips overlap (the loop is latency bound).
     constexpr int U = 4;
-    auto cd_batch = [&](const int (&gv)[U], const bool (&ok)[U], size_t orow, int xb) {
+    auto cd_batch = [&](const int (&gv)[U], const bool (&ok)[U], const unsigned (&ofs)[U]) {
         float m[U], v[U];
         const bool calib = (ops & CVB_SQ_CD_CALIBRATE) != 0;
         if (!calib && !has_cd) return;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const size_t o = orow + xb + 32 * j;
+            const unsigned o = ofs[j];
             if (calib) { m[j] = (float)gv[j]; v[j] = initvar; }
             else if (ok[j]) { m[j] = cd_mean[o]; v[j] = cd_var[o]; }
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             if (!ok[j]) continue;
-            const size_t o = orow + xb + 32 * j;
+            const unsigned o = ofs[j];
             const float gf = (float)gv[j];
             if (calib) { cd_mean[o] = m[j]; cd_var[o] = v[j]; flags[o] |= 2; }
             if (ops & CVB_SQ_CD_DETECT) {
@@ -316,67 +327,70 @@ __global__ void __launch_bounds__(256, 4) k_squares(const SquareArgs a)
 
     if (pass1) {
         const bool k5 = a.p.pd_blur == 5;
-        for (int y = warp; y < h; y += 8) {
-            const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
-            for (int xb = lane; xb < w; xb += 32 * U) {
-                int gv[U], mk[U], rf[U];
-                bool ok[U];
+        for (int i0 = tid; i0 < n; i0 += 256 * U) {
+            int gv[U], mk[U], rf[U];
+            bool ok[U];
+            unsigned ofs[U];
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    const int x = xb + 32 * j;
-                    ok[j] = x < w;
-                    mk[j] = 0; rf[j] = 0; gv[j] = 0;
-                    if (ok[j]) {
-                        if (ops & CVB_SQ_PD_STATS) {
-                            mk[j] = mask[y * w + x];
-                            if (has_ref) rf[j] = pd_ref[orow + x];
-                        }
-                        gv[j] = k5 ? blur_at<5>(s_h, a.pd_q, 5, x, y, w, h, near_pd)
-                                   : blur_at<0>(s_h, a.pd_q, a.p.pd_blur, x, y, w, h, near_pd);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    if (!ok[j]) continue;
-                    const size_t o = orow + xb + 32 * j;
-                    const int g1 = gv[j];
+            for (int j = 0; j < U; ++j) {
+                const int i = i0 + 256 * j;
+                ok[j] = i < n;
+                mk[j] = 0; rf[j] = 0; gv[j] = 0; ofs[j] = 0;
+                if (ok[j]) {
+                    const int y = div_magic(i, inv_w), x = i - y * w;
+                    ofs[j] = (unsigned)(y * a.BW + x);
                     if (ops & CVB_SQ_PD_STATS) {
-                        const int m = mk[j];
-                        sum += g1; sumsq += (unsigned)(g1 * g1);
-                        if (has_ref) sad += (unsigned)abs(g1 - rf[j]);
-                        if (m & 1) { csum += g1; ++ccnt; }
-                        if (m & 2) { bsum += g1; ++bcnt; }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (m & (4 << k)) { rsum[k] += g1; ++rcnt[k]; }
+                        mk[j] = mask[i];
+                        if (has_ref) rf[j] = pd_ref[ofs[j]];
                     }
-                    if (state && need_pd) pd_cur[o] = (uint8_t)g1;
-                    if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { pd_ref[o] = (uint8_t)g1; flags[o] |= 1; }
+                    gv[j] = k5 ? blur_at<5>(s_h, a.pd_q, 5, x, y, w, h, near_pd)
+                               : blur_at<0>(s_h, a.pd_q, a.p.pd_blur, x, y, w, h, near_pd);
                 }
-                if (need_cd && same_blur) cd_batch(gv, ok, orow, xb);
             }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                if (!ok[j]) continue;
+                const unsigned o = ofs[j];
+                const int g1 = gv[j];
+                if (ops & CVB_SQ_PD_STATS) {
+                    const int m = mk[j];
+                    sum += g1; sumsq += (unsigned)(g1 * g1);
+                    if (has_ref) sad += (unsigned)abs(g1 - rf[j]);
+                    if (m & 1) { csum += g1; ++ccnt; }
+                    if (m & 2) { bsum += g1; ++bcnt; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (m & (4 << k)) { rsum[k] += g1; ++rcnt[k]; }
+                }
+                if (state && need_pd) pd_cur[o] = (uint8_t)g1;
+                if ((ops & CVB_SQ_PD_SET_REF) && selected && state) { pd_ref[o] = (uint8_t)g1; flags[o] |= 1; }
+            }
+            if (need_cd && same_blur) cd_batch(gv, ok, ofs);
         }
     }
     // ---- ChangeDetector pass when its blur differs ----
     if (need_cd && !same_blur) {
         __syncthreads();
-        if (a.p.cd_blur == 5) hpass<5>(s_g, s_h, a.cd_q, 5, w, h, near_cd);
-        else hpass<0>(s_g, s_h, a.cd_q, a.p.cd_blur, w, h, near_cd);
+        if (a.p.cd_blur == 5) hpass<5>(s_g, s_h, a.cd_q, 5, w, h, inv_w, near_cd);
+        else hpass<0>(s_g, s_h, a.cd_q, a.p.cd_blur, w, h, inv_w, near_cd);
         __syncthreads();
-        for (int y = warp; y < h; y += 8) {
-            const size_t orow = so + (size_t)(rc.y + y) * a.BW + rc.x;
-            for (int xb = lane; xb < w; xb += 32 * U) {
-                int gv[U];
-                bool ok[U];
+        for (int i0 = tid; i0 < n; i0 += 256 * U) {
+            int gv[U];
+            bool ok[U];
+            unsigned ofs[U];
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    const int x = xb + 32 * j;
-                    ok[j] = x < w;
-                    gv[j] = !ok[j] ? 0 : a.p.cd_blur == 5 ? blur_at<5>(s_h, a.cd_q, 5, x, y, w, h, near_cd)
-                                                           : blur_at<0>(s_h, a.cd_q, a.p.cd_blur, x, y, w, h, near_cd);
+            for (int j = 0; j < U; ++j) {
+                const int i = i0 + 256 * j;
+                ok[j] = i < n;
+                gv[j] = 0; ofs[j] = 0;
+                if (ok[j]) {
+                    const int y = div_magic(i, inv_w), x = i - y * w;
+                    ofs[j] = (unsigned)(y * a.BW + x);
+                    gv[j] = a.p.cd_blur == 5 ? blur_at<5>(s_h, a.cd_q, 5, x, y, w, h, near_cd)
+                                             : blur_at<0>(s_h, a.cd_q, a.p.cd_blur, x, y, w, h, near_cd);
                 }
-                cd_batch(gv, ok, orow, xb);
             }
+            cd_batch(gv, ok, ofs);
         }
     }
     if (!a.stats) return;

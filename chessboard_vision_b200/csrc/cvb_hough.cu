@@ -43,10 +43,6 @@ struct HoughMisc {
     unsigned long long best[HW_];
 };
 
-// i / d for i * d < 2^32 with inv = floor((2^32 - 1) / d) + 1 (one IMAD.HI instead of a division)
-CVB_DEV int div_magic(int i, unsigned inv) { return inv ? (int)__umulhi((unsigned)i, inv) : i; }
-CVB_DEV unsigned magic_of(int d) { return d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u; }
-
 CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
 {
     // g has a one-pixel replicated border: pixel (y, x) sits at g[(y + 1) * gp + x + 1]
