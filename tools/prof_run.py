@@ -1,5 +1,6 @@
 """Short device-resident run of the whole path for ncu (no CPU leg, no e2e leg).
-usage: python tools/prof_run.py [frames] [steps]"""
+usage: python tools/prof_run.py [frames] [steps]      (CVB_HOUGH=1 adds the Hough-circle launch on the squares of every frame,
+CVB_CHECK=1 a small parity check against the oracle)"""
 import os
 import sys
 
@@ -27,6 +28,8 @@ eng.synchronize()
 eng.profile(True)
 for _ in range(steps):
     eng.pipeline_dev(d_in, M, rects, run, st, stats=d_stats, otsu_t=d_otsu)
+    if os.environ.get("CVB_HOUGH"):
+        eng.hough_state(st, rects, None, 0, n)
 prof = eng.profile_read()
 tot = sum(v[0] for v in prof.values())
 for k, (ms, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
