@@ -44,9 +44,11 @@ CVB_DEV void bgr2lab_px(const SmemColorTables *t, int b, int g, int r, int &L, i
     const int fX = t->cbrt[(Rl * 1777 + Gl * 1541 + Bl * 778 + 2048) >> 12];
     const int fY = t->cbrt[(Rl * 871 + Gl * 2929 + Bl * 296 + 2048) >> 12];
     const int fZ = t->cbrt[(Rl * 73 + Gl * 448 + Bl * 3575 + 2048) >> 12];
-    L = clamp_u8((296 * fY - 1336934 + 16384) >> 15);
-    A = clamp_u8((500 * (fX - fY) + 128 * 32768 + 16384) >> 15);
-    Bc = clamp_u8((200 * (fY - fZ) + 128 * 32768 + 16384) >> 15);
+    // OpenCV saturates these to 0..255; over all 2^24 inputs the values stay inside L 0..255, a 42..226,
+    // b 20..223 (tests/test_abi.py::test_lab_forward_never_saturates), so the clamps are dropped
+    L = (296 * fY - 1336934 + 16384) >> 15;
+    A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
 }
 
 // abToXZ_b as a function (C integer division truncates toward zero)
@@ -71,6 +73,10 @@ CVB_DEV uint32_t lab2bgr_px(const SmemColorTables *t, int L, int a, int b)
     return pack_bgr(t->invgamma[bo], t->invgamma[go], t->invgamma[ro]);
 }
 
+// The CLAHE blend is a convex combination of four bytes with f32 weights a, 1 - a: it lies in [0, 255 * (1 + 2^-22)],
+// so saturate_cast<uchar> reduces to the rounding
+CVB_DEV int blend_u8(float v) { return __float2int_rn(v); }
+
 // S2 interpolation (clahe.cpp CLAHE_Interpolation_Body); unfused f32, this association
 struct ClaheAxis { int i1, i2; float a, a1; };
 CVB_DEV ClaheAxis clahe_axis(int p, float inv_t, int tiles)
@@ -92,7 +98,7 @@ CVB_DEV int clahe_interp(const uint8_t *__restrict__ lut, int tiles_x, const Cla
     const float l22 = (float)__ldg(lut + (ay.i2 * tiles_x + ax.i2) * 256 + v);
     const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, ax.a1), __fmul_rn(l12, ax.a)), ay.a1);
     const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, ax.a1), __fmul_rn(l22, ax.a)), ay.a);
-    return round_u8(__fadd_rn(top, bot));
+    return blend_u8(__fadd_rn(top, bot));
 }
 
 // S7: RGB2Gray<uchar>, 15-bit coefficients -- frame_enhancer.py:154

@@ -387,9 +387,10 @@ __host__ __device__ constexpr int r2_class(int r2)
 }
 static const int kR2[10] = {0, 1, 2, 4, 5, 8, 9, 10, 13, 16};
 
-struct __align__(8) AxisInfo {   // one per staged column / row: a single 64-bit shared load
+struct __align__(16) AxisInfo {  // one per staged column / row: a single 128-bit shared load
     float a;                     // CLAHE blend factor towards the second tile (a1 = 1 - a)
-    uint32_t packed;             // mirrored source coordinate (low 16) | first tile index << 16 | second << 24
+    uint32_t src;                // byte offset of the mirrored source column in a row (x * 3) / of the source row in the frame
+    uint32_t t1, t2;             // byte offsets of the two CLAHE tile LUTs along this axis (column: tile * 256, row: tile * tiles_x * 256)
 };
 
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int LUTMODE = 1>
@@ -448,11 +449,13 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         const bool col = i < AW;
         const int p = col ? reflect101(ax0 + i, W) : reflect101(ay0 + (i - AW), H);
         ai.a = 0.f;
-        ai.packed = (uint32_t)p;
+        ai.src = col ? (uint32_t)p * 3u : (uint32_t)p * (uint32_t)W * 3u;       // a frame is < 4 GB
+        ai.t1 = ai.t2 = 0;
         if (LIGHT) {
             const ClaheAxis ca = col ? clahe_axis(p, a.g.inv_tw, a.g.tiles_x) : clahe_axis(p, a.g.inv_th, a.g.tiles_y);
+            const uint32_t unit = col ? 256u : 256u * (uint32_t)a.g.tiles_x;
             ai.a = ca.a;
-            ai.packed |= ((uint32_t)ca.i1 << 16) | ((uint32_t)ca.i2 << 24);
+            ai.t1 = (uint32_t)ca.i1 * unit; ai.t2 = (uint32_t)ca.i2 * unit;
         }
         sAx[i] = ai;
     }
@@ -476,22 +479,19 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         for (int i = tid; i < AW * AH; i += NT) {
             const int ly = i / AW, lx = i - ly * AW;
             const AxisInfo cx = sAx[lx], cy = sAx[AW + ly];
-            const int sx = cx.packed & 0xffff, sy = cy.packed & 0xffff;
-            const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
+            const uint8_t *p = img + (cy.src + cx.src);                 // 32-bit sum: one 64-bit add per pixel
             const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
             uint32_t q;
             if (LIGHT) {
                 int L, A, B;
                 bgr2lab_px(sTab, c0, c1, c2, L, A, B);
-                const int tx1 = (cx.packed >> 16) & 0xff, tx2 = cx.packed >> 24;
-                const uint8_t *l1 = lut + (((cy.packed >> 16) & 0xff) * a.g.tiles_x << 8) + L;
-                const uint8_t *l2 = lut + ((cy.packed >> 24) * a.g.tiles_x << 8) + L;
-                const float l11 = (float)__ldg(l1 + (tx1 << 8)), l12 = (float)__ldg(l1 + (tx2 << 8));
-                const float l21 = (float)__ldg(l2 + (tx1 << 8)), l22 = (float)__ldg(l2 + (tx2 << 8));
+                const uint32_t o1 = cy.t1 + (uint32_t)L, o2 = cy.t2 + (uint32_t)L;
+                const float l11 = (float)__ldg(lut + (o1 + cx.t1)), l12 = (float)__ldg(lut + (o1 + cx.t2));
+                const float l21 = (float)__ldg(lut + (o2 + cx.t1)), l22 = (float)__ldg(lut + (o2 + cx.t2));
                 const float xa1 = __fsub_rn(1.0f, cx.a), ya1 = __fsub_rn(1.0f, cy.a);
                 const float top = __fmul_rn(__fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, cx.a)), ya1);
                 const float bot = __fmul_rn(__fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, cx.a)), cy.a);
-                L = round_u8(__fadd_rn(top, bot));
+                L = blend_u8(__fadd_rn(top, bot));
                 q = lab2bgr_px(sTab, L, A, B);
             } else {
                 q = pack_bgr(c0, c1, c2);

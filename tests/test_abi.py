@@ -109,3 +109,26 @@ def test_product_does_not_import_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "cvb_oracle" not in txt, f
+
+
+def test_lab_forward_never_saturates():
+    """The kernels compute L, a, b of RGB2Lab_b without OpenCV's saturate_cast: exhaustively, over all 2^24
+    inputs and the library's own tables, the unclamped values stay inside 0..255."""
+    import numpy as np
+    lib = _lib.load()
+    gamma = np.zeros(256, np.uint16); cbrt = np.zeros(2048, np.uint16); yf = np.zeros(512, np.int32)
+    inv = np.zeros(4096, np.uint8); lt = np.zeros(2048, np.uint8)
+    assert lib.cvb_get_tables(gamma.ctypes.data, cbrt.ctypes.data, yf.ctypes.data, inv.ctypes.data, lt.ctypes.data) == 0
+    g = gamma.astype(np.int64)
+    G, R = np.meshgrid(g, g, indexing="ij")
+    lo, hi = [10 ** 9] * 3, [-10 ** 9] * 3
+    for b in range(256):
+        Bl = g[b]
+        fX = cbrt[(R * 1777 + G * 1541 + Bl * 778 + 2048) >> 12].astype(np.int64)
+        fY = cbrt[(R * 871 + G * 2929 + Bl * 296 + 2048) >> 12].astype(np.int64)
+        fZ = cbrt[(R * 73 + G * 448 + Bl * 3575 + 2048) >> 12].astype(np.int64)
+        vals = ((296 * fY - 1336934 + 16384) >> 15, (500 * (fX - fY) + 128 * 32768 + 16384) >> 15,
+                (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15)
+        for k, v in enumerate(vals):
+            lo[k] = min(lo[k], int(v.min())); hi[k] = max(hi[k], int(v.max()))
+    assert (lo, hi) == ([0, 42, 20], [255, 226, 223])
