@@ -6,8 +6,7 @@
 //   A  Sobel 3x3 (replicate border), Canny(dx, dy, max(1, param1/2), param1) with L1 magnitude
 //   B  every edge pixel with a non-zero gradient walks a Q10 ray along +-gradient for the radii
 //      minRadius..maxRadius through an accumulator of 1/dp resolution; a ray stops at its first
-//      step outside.  The in-range steps of a straight ray through a box form an interval, so
-//      "step r votes" == "step minRadius and step r are inside": the rays are voted step-parallel
+//      step outside (one thread per ray, shared-memory atomics)
 //   C  centres: cells (not in accumulator row 0 / column 0) > param2, > left, >= right, > up, >= down
 //   D  per centre (one warp each): distances to the edge pixels, 10 bins per dp, best 10-bin
 //      window scanning downwards -> (radius, support); kept when support > param2
@@ -183,27 +182,23 @@ __global__ void __launch_bounds__(HNT, 4) k_hough(const uint8_t *__restrict__ pl
         }
         __syncthreads();
     }
-    {
-        const int span = max_r - min_r + 1;
-        // one warp per ray (pixel, direction): lanes take the radius steps
-        for (int ray = warp; ray < 2 * nnz; ray += HW_) {
-            const int p = nz[ray >> 1], x = p & 255, y = p >> 8;
-            int sx, sy;
-            if (dir_stored) {
-                const int d = s_dir[ray >> 1];
-                sx = (int)(short)(d & 0xffff); sy = d >> 16;
-            } else {
-                ray_step(x, y, sx, sy);
-            }
-            if (ray & 1) { sx = -sx; sy = -sy; }
-            const int x0 = __float2int_rn(__fmul_rn(__fmul_rn((float)x, idp), 1024.f));
-            const int y0 = __float2int_rn(__fmul_rn(__fmul_rn((float)y, idp), 1024.f));
-            const int xs = (x0 + min_r * sx) >> 10, ys = (y0 + min_r * sy) >> 10;
-            if ((unsigned)xs >= (unsigned)acols || (unsigned)ys >= (unsigned)arows) continue;
-            for (int k = lane; k < span; k += 32) {
-                const int x2 = (x0 + (min_r + k) * sx) >> 10, y2 = (y0 + (min_r + k) * sy) >> 10;
-                if ((unsigned)x2 < (unsigned)acols && (unsigned)y2 < (unsigned)arows) atomicAdd(&acc[y2 * astep + x2], 1);
-            }
+    // one thread per ray (pixel, direction), walking it until its first step outside the accumulator
+    for (int ray = tid; ray < 2 * nnz; ray += HNT) {
+        const int p = nz[ray >> 1], x = p & 255, y = p >> 8;
+        int sx, sy;
+        if (dir_stored) {
+            const int d = s_dir[ray >> 1];
+            sx = (int)(short)(d & 0xffff); sy = d >> 16;
+        } else {
+            ray_step(x, y, sx, sy);
+        }
+        if (ray & 1) { sx = -sx; sy = -sy; }
+        int x1 = __float2int_rn(__fmul_rn(__fmul_rn((float)x, idp), 1024.f)) + min_r * sx;
+        int y1 = __float2int_rn(__fmul_rn(__fmul_rn((float)y, idp), 1024.f)) + min_r * sy;
+        for (int r = min_r; r <= max_r; ++r, x1 += sx, y1 += sy) {
+            const int x2 = x1 >> 10, y2 = y1 >> 10;
+            if ((unsigned)x2 >= (unsigned)acols || (unsigned)y2 >= (unsigned)arows) break;
+            atomicAdd(&acc[y2 * astep + x2], 1);
         }
     }
     __syncthreads();      // gray / mag / map are dead from here on: the union switches to its late view
