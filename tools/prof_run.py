@@ -29,11 +29,14 @@ eng.profile(True)
 for _ in range(steps):
     eng.pipeline_dev(d_in, M, rects, run, st, stats=d_stats, otsu_t=d_otsu)
     if os.environ.get("CVB_HOUGH"):
-        eng.hough_state(st, rects, None, 0, n)
+        hres = eng.hough_state(st, rects, None, 0, n)
 prof = eng.profile_read()
 tot = sum(v[0] for v in prof.values())
 for k, (ms, c) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
     print("%-16s %8.3f ms/launch  %5.1f%%  (%.2f us/frame)" % (k, ms / c, 100 * ms / tot, ms / c / n * 1e3))
+if os.environ.get("CVB_HOUGH"):
+    print("hough: %.0f edge pixels, %.1f candidate centres, %.2f circles per square" % (
+        hres["n_edges"].mean(), hres["n_centers"].mean(), hres["count"].mean()))
 print("total %.3f ms/step  -> %.0f frames/s" % (tot / steps, n * steps / tot * 1e3))
 if os.environ.get("CVB_CHECK"):
     import oracle as O
