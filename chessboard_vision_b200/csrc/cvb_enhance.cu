@@ -558,9 +558,14 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
                         for (int dx = -4; dx <= 4; ++dx) {
                             if (dy * dy + dx * dx > 16) continue;
                             const int c = j + 4 + dx;
-                            const unsigned sad = __vsadu4(px[c], ctr[t][j]);
-                            const float w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
-                                                         : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
+                            float w;
+                            if (dy == 0 && dx == 0) {
+                                w = 1.0f;      // the centre tap: distance 0 in space and colour, exp(0) * exp(0)
+                            } else {
+                                const unsigned sad = __vsadu4(px[c], ctr[t][j]);
+                                w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
+                                                 : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
+                            }
                             wsum[t][j] = __fadd_rn(wsum[t][j], w);
                             sb[t][j] = __fmaf_rn(fb[c], w, sb[t][j]);
                             sg[t][j] = __fmaf_rn(fg[c], w, sg[t][j]);
