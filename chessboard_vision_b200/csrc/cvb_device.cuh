@@ -160,6 +160,34 @@ CVB_DEV int warp_max(int v)
     return v;
 }
 
+// ---- TMA bulk copy (cp.async.bulk) of a 16-byte-aligned table into shared memory -------------
+// One thread arms an mbarrier with the byte count and issues the copy; the copy engine moves the bytes and
+// completes the barrier's transaction; readers wait on the barrier's phase.  No thread touches the data on the way.
+CVB_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CVB_DEV void mbar_init(uint64_t *bar, int arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+CVB_DEV void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+CVB_DEV void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+CVB_DEV void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(phase)
+        : "memory");
+}
+
 // ---- byte-span staging between global and shared memory ---------------------------
 // Copies nbytes from g into a 16B-aligned shared buffer so that g[i] lands at
 // s_base[phase + i] with phase = (address of g) & 15: the 16-byte body then moves

@@ -438,11 +438,14 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     const int bx0 = x0 - Cfg::BX, by0 = y0 - Cfg::BY, ax0 = bx0 - AR, ay0 = by0 - AR;
     const uint8_t *img = a.src + (size_t)frame * H * W * 3;
 
-    if (LIGHT) load_color_tables(sTab, a.tabs);
-    if (BIL) {
-        const uint4 *gw = reinterpret_cast<const uint4 *>(a.wlut);
-        uint4 *dw = reinterpret_cast<uint4 *>(smem_raw + Cfg::offW);
-        for (int i = tid; i < Cfg::NLUT * 768 / 4; i += NT) dw[i] = __ldg(gw + i);
+    // The two constant tables come in through the copy engine (TMA bulk copies): the colour-conversion tables are
+    // awaited before stage A, the bilateral weight table before stage B, whose load so overlaps stage A.
+    __shared__ uint64_t s_bar[2];
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        mbar_init_fence();
+        if (LIGHT) bulk_g2s(sTab, a.tabs, (uint32_t)sizeof(SmemColorTables), &s_bar[0]);
+        if (BIL) bulk_g2s(smem_raw + Cfg::offW, a.wlut, (uint32_t)(Cfg::NLUT * 768 * 4), &s_bar[1]);
     }
     for (int i = tid; i < AW + AH; i += NT) {
         AxisInfo ai;
@@ -472,6 +475,7 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         }
     }
     __syncthreads();
+    if (LIGHT) mbar_wait(&s_bar[0], 0);
 
     // ---- A ----
     {
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     __syncthreads();
 
     // ---- B ----
+    if (BIL) mbar_wait(&s_bar[1], 0);
     // ROWS output rows per thread: a window row is loaded and converted to float once and feeds every output
     // row of the thread it is in range of (ROWS == 2 halves the byte->float conversions and the LDS.128s).
     if (BIL) {
