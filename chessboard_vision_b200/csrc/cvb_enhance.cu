@@ -405,8 +405,12 @@ struct FusedCfg {
     static constexpr size_t offB = offA + (size_t)AW * AH * 4;
     static constexpr size_t offW = offB + (BIL ? (size_t)BW * BH * 4 : 0);
     static constexpr int NLUT = LUTMODE == 1 ? 10 : 1;
-    static constexpr size_t offT = offW + (BIL ? NLUT * 768 * 4 : 0);
-    static constexpr size_t offX = offT + (LIGHT ? sizeof(SmemColorTables) : 0);
+    // the colour-conversion tables are only read in stage A, the B tile only written from stage B on: with a
+    // bilateral stage they share memory
+    static constexpr bool TAB_IN_B = BIL && LIGHT && (size_t)BW * BH * 4 >= sizeof(SmemColorTables);
+    static constexpr size_t endW = offW + (BIL ? NLUT * 768 * 4 : 0);
+    static constexpr size_t offT = TAB_IN_B ? offB : endW;
+    static constexpr size_t offX = endW + (LIGHT && !TAB_IN_B ? sizeof(SmemColorTables) : 0);
     static constexpr size_t smem_bytes = offX + (size_t)(AW + AH) * sizeof(AxisInfo) + (size_t)(2 * TW + 2 * TH) * 2;
 };
 
@@ -726,12 +730,14 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     }
     memset(a.sw, 0, sizeof a.sw);
     if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
-    // Tile shapes measured on B200 at 1080p (profiles/r01_notes.md): 120x60 outputs per 512-thread CTA tile 1080p and
-    // 4K exactly and keep the halo overheads low (B 1.10x, A 1.28x); the folded 30 KB weight table beat the 3 KB one.
-    if (light && bilateral && sharpen) return launch_fused_t<120, 60, true, true, true, 512, 1, 2>(h, a, n);
-    if (!light && bilateral && !sharpen) return launch_fused_t<120, 60, false, true, false, 512, 1, 2>(h, a, n);
-    if (!light && bilateral && sharpen) return launch_fused_t<120, 60, false, true, true, 512, 1, 2>(h, a, n);
-    if (light && bilateral && !sharpen) return launch_fused_t<120, 60, true, true, false, 512, 1, 2>(h, a, n);
+    // Tile shapes measured on B200 at 1080p (profiles/r01_notes.md): 120x64 outputs per 512-thread CTA.  With the
+    // sharpen halo the bilateral stage then has 31 runs x 33 row pairs = 1023 work items for its two rounds of 512
+    // threads, the sharpen stage exactly 15 pixels per thread; two CTAs fit an SM because the colour tables share
+    // memory with the B tile.  The folded 30 KB weight table beat the 3 KB one.
+    if (light && bilateral && sharpen) return launch_fused_t<120, 64, true, true, true, 512, 1, 2>(h, a, n);
+    if (!light && bilateral && !sharpen) return launch_fused_t<120, 64, false, true, false, 512, 1, 2>(h, a, n);
+    if (!light && bilateral && sharpen) return launch_fused_t<120, 64, false, true, true, 512, 1, 2>(h, a, n);
+    if (light && bilateral && !sharpen) return launch_fused_t<120, 64, true, true, false, 512, 1, 2>(h, a, n);
     if (!light && !bilateral && sharpen) return launch_fused_t<60, 30, false, false, true>(h, a, n);
     if (light && !bilateral && !sharpen) return launch_fused_t<60, 30, true, false, false>(h, a, n);
     cvb_set_error("unsupported fused stage combination");
