@@ -599,9 +599,81 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
         __syncthreads();
     }
 
-    // ---- C ----  (results of the tile go to sOut = the start of sA, free once B is done)
-    uint32_t *sOut = sA;
+    // ---- C ----
     int vmin = 255, vmax = 0;
+    // Sharpen, fast path (aligned rows, tile not cut on the right): the one-pixel ring of the B tile that lies outside
+    // the image is first filled with its REFLECT_101 mirror, then a thread sharpens 4 pixels of a row from two LDS.128
+    // per neighbour row (column sums shared between the 4 outputs) and stores its 12 bytes straight to the frame.
+    const bool fastC = SHARP && BIL && (W % 4 == 0) && (x0 + TW <= W) && W >= 2 && H >= 2 &&
+                       ((reinterpret_cast<uintptr_t>(a.dst) & 3) == 0);
+    if (fastC) {
+        constexpr int BX = Cfg::BX, BY = Cfg::BY;
+        const int vh = min(TH, H - y0);                        // valid output rows of this tile
+        const bool top = y0 == 0, bottom = y0 + vh == H, left = x0 == 0, right = x0 + TW == W;
+        if (top || bottom) {
+            for (int i = tid; i < BW; i += NT) {
+                if (top) sB[(BY - 1) * BW + i] = sB[(BY + 1) * BW + i];
+                if (bottom) sB[(BY + vh) * BW + i] = sB[(BY + vh - 2) * BW + i];
+            }
+            __syncthreads();
+        }
+        if (left || right) {
+            for (int i = tid; i < vh + 2; i += NT) {
+                uint32_t *row = sB + (BY - 1 + i) * BW;
+                if (left) row[BX - 1] = row[BX + 1];
+                if (right) row[BX + TW] = row[BX + TW - 2];
+            }
+            __syncthreads();
+        }
+        uint8_t *out = a.dst + (size_t)frame * H * W * 3;
+        constexpr int GROUPS = TW / 4;
+        for (int item = tid; item < TH * GROUPS; item += NT) {
+            const int ty = item / GROUPS, tx4 = (item - ty * GROUPS) * 4;
+            if (ty >= vh) break;
+            // columns tx4 .. tx4+7 of the B tile = image x - 2 .. x + 5 for the group's first pixel x (BX == 2)
+            uint32_t cbr[6], cg[6], ctr_w[4];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cbr[k] = cg[k] = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const uint32_t *rp = sB + (ty + BY - 1 + r) * BW + tx4;
+                const uint4 q0 = *reinterpret_cast<const uint4 *>(rp), q1 = *reinterpret_cast<const uint4 *>(rp + 4);
+                const uint32_t w[6] = {q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};      // image x - 1 .. x + 4
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { cbr[k] += w[k] & 0x00ff00ffu; cg[k] += (w[k] >> 8) & 0xffu; }
+                if (r == 1) { ctr_w[0] = w[1]; ctr_w[1] = w[2]; ctr_w[2] = w[3]; ctr_w[3] = w[4]; }
+            }
+            uint32_t res[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // 16-bit lanes: (b, r) in one word, g in the other; nine bytes sum to <= 2295
+                const uint32_t s02 = cbr[j] + cbr[j + 1] + cbr[j + 2], s1 = cg[j] + cg[j + 1] + cg[j + 2];
+                const uint32_t c = ctr_w[j];
+                const int b = clamp_u8(10 * (int)(c & 0xff) - (int)(s02 & 0xffff));
+                const int g = clamp_u8(10 * (int)((c >> 8) & 0xff) - (int)s1);
+                const int r = clamp_u8(10 * (int)((c >> 16) & 0xff) - (int)(s02 >> 16));
+                res[j] = pack_bgr(b, g, r);
+                if (a.minmax) {
+                    vmin = min(vmin, min(b, min(g, r)));
+                    vmax = max(vmax, max(b, max(g, r)));
+                }
+            }
+            uint32_t *o32 = reinterpret_cast<uint32_t *>(out + ((size_t)(y0 + ty) * W + x0 + tx4) * 3);
+            o32[0] = (res[0] & 0xffffffu) | (res[1] << 24);
+            o32[1] = ((res[1] >> 8) & 0xffffu) | (res[2] << 16);
+            o32[2] = ((res[2] >> 16) & 0xffu) | (res[3] << 8);
+        }
+        if (a.minmax) {
+            vmin = warp_min(vmin); vmax = warp_max(vmax);
+            if ((tid & 31) == 0) {
+                atomicMin(a.minmax + 2 * frame, vmin);
+                atomicMax(a.minmax + 2 * frame + 1, vmax);
+            }
+        }
+        return;
+    }
+    // general path (results of the tile go to sOut = the start of sA, free once B is done)
+    uint32_t *sOut = sA;
     uint32_t keep[(TW * TH + NT - 1) / NT];
 #pragma unroll
     for (int it = 0; it < (TW * TH + NT - 1) / NT; ++it) {
