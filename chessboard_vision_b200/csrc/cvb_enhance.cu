@@ -423,6 +423,9 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
 #ifndef CONV_MIX
 #define CONV_MIX 1
 #endif
+#ifndef CONV_PAIR
+#define CONV_PAIR 1
+#endif
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
 __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
@@ -552,8 +555,18 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 #pragma unroll
                 for (int c = 0; c < 12; ++c) {
                     if (c < lo || c > 11 - lo) continue;
+#if CONV_PAIR
+                    {   // two byte->float conversions share one packed add (FADD2): 2 PRMT + 1 FADD2 instead of 2 PRMT + 2 FADD
+                        unsigned long long pr, res;
+                        const uint32_t mb = __byte_perm(px[c], 0x4B000000u, 0x7540u), mg = __byte_perm(px[c], 0x4B000000u, 0x7541u);
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(pr) : "r"(mb), "r"(mg));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(res) : "l"(pr), "l"(0xCB000000CB000000ull));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(fb[c]), "=f"(fg[c]) : "l"(res));
+                    }
+#else
                     fb[c] = byte_to_float(px[c], 0);
                     fg[c] = byte_to_float(px[c], 1);
+#endif
                     // one channel goes through the otherwise idle conversion unit (I2F.U8): one issue slot instead of two
                     fr[c] = CONV_MIX ? (float)((px[c] >> 16) & 0xffu) : byte_to_float(px[c], 2);
                 }
