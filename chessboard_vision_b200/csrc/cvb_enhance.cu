@@ -427,7 +427,7 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
 #define CONV_PAIR 1
 #endif
 template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
-__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) k_fused(const FusedArgs a)
+__global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
