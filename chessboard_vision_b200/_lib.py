@@ -129,6 +129,9 @@ SYMBOLS = [
     ("cvb_warp_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     ("cvb_warp_rot180_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     ("cvb_rotate_dev", _I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    ("cvb_gaussian_sigma_dev", _I, [_P, _P, _I, _I, _I, _I, _D, _P]),
+    ("cvb_dilate_dev", _I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    ("cvb_contour_mask_dev", _I, [_P, _P, _I, _I, _I, _P]),
     ("cvb_canny_dev", _I, [_P, _P, _I, _I, _I, _D, _D, _P]),
     ("cvb_projections_dev", _I, [_P, _P, _I, _I, _I, _P, _P]),
     ("cvb_state_create", _I, [_P, _I, _I, _I, C.POINTER(_P)]),

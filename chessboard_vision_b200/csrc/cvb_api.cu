@@ -402,7 +402,13 @@ int cvb_gaussian_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, i
 {
     REQ_H(h); REQ_IMG(n, H, W);
     CVB_REQUIRE(plane && out && plane != out, "null or aliased image pointer");
-    return launch_gaussian(h, plane, n, H, W, ksize, out);
+    return launch_gaussian(h, plane, n, H, W, ksize, 0.0, out);
+}
+int cvb_gaussian_sigma_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, int ksize, double sigma, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(plane && out && plane != out, "null or aliased image pointer");
+    return launch_gaussian(h, plane, n, H, W, ksize, sigma, out);
 }
 
 static int analysis_tail(cvb_handle *h, const uint8_t *src, const int32_t *minmax, int n, int H, int W,
@@ -556,6 +562,25 @@ int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W, doubl
     REQ_H(h); REQ_IMG(n, H, W);
     CVB_REQUIRE(gray && edges, "null image pointer");
     return launch_canny(h, gray, n, H, W, low_thresh, high_thresh, edges);
+}
+int cvb_dilate_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, int kw, int kh, int iterations, uint8_t *out)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(plane && out && plane != out, "null or aliased image pointer");
+    CVB_REQUIRE(kw >= 1 && kh >= 1 && (kw & 1) && (kh & 1) && iterations >= 1, "dilate: odd kernel sizes and iterations >= 1");
+    return launch_dilate(h, plane, n, H, W, kw, kh, iterations, out);
+}
+int cvb_contour_mask_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *mask)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr && mask, "null image pointer");
+    const size_t npx = (size_t)H * W;
+    WS(ws_gray, uint8_t, npx * n, gray);
+    WS(ws_blur, uint8_t, npx * n, blur);
+    CVB_TRY(launch_gray(h, bgr, (long)npx * n, gray));
+    CVB_TRY(launch_gaussian(h, gray, n, H, W, 7, 1.0, blur));
+    CVB_TRY(launch_canny(h, blur, n, H, W, 30, 100, gray));
+    return launch_dilate(h, gray, n, H, W, 5, 5, 3, mask);
 }
 int cvb_projections_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W, uint32_t *row_sums, uint32_t *col_sums)
 {

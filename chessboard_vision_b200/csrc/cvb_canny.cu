@@ -124,7 +124,52 @@ __global__ void __launch_bounds__(256) k_projections(const uint8_t *__restrict__
     }
 }
 
+// cv2.dilate with a kw x kh rectangle, `iterations` times = one max filter of radius (rx, ry); positions outside the
+// image do not take part (morphologyDefaultBorderValue).  64 x 16 output tile, rows then columns in shared memory.
+constexpr int DT_W = 64, DT_H = 16, D_MAXR = 24;
+__global__ void __launch_bounds__(256) k_dilate(const uint8_t *__restrict__ src, int H, int W, int rx, int ry, uint8_t *__restrict__ dst)
+{
+    __shared__ uint8_t s_in[DT_H + 2 * D_MAXR][DT_W + 2 * D_MAXR];
+    __shared__ uint8_t s_row[DT_H + 2 * D_MAXR][DT_W];
+    const int frame = blockIdx.z, x0 = blockIdx.x * DT_W, y0 = blockIdx.y * DT_H;
+    const uint8_t *img = src + (size_t)frame * H * W;
+    const int iw = DT_W + 2 * rx, ih = DT_H + 2 * ry;
+    for (int i = threadIdx.x; i < iw * ih; i += 256) {
+        const int ly = i / iw, lx = i - ly * iw, y = y0 - ry + ly, x = x0 - rx + lx;
+        s_in[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? img[(size_t)y * W + x] : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DT_W * ih; i += 256) {
+        const int ly = i / DT_W, lx = i - ly * DT_W;
+        int m = 0;
+        for (int k = 0; k <= 2 * rx; ++k) m = max(m, (int)s_in[ly][lx + k]);
+        s_row[ly][lx] = (uint8_t)m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DT_W * DT_H; i += 256) {
+        const int ly = i / DT_W, lx = i - ly * DT_W, y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        int m = 0;
+        for (int k = 0; k <= 2 * ry; ++k) m = max(m, (int)s_row[ly + k][lx]);
+        dst[(size_t)frame * H * W + (size_t)y * W + x] = (uint8_t)m;
+    }
+}
+
 }  // namespace
+
+int launch_dilate(cvb_handle *h, const uint8_t *src, int n, int H, int W, int kw, int kh, int iterations, uint8_t *dst)
+{
+    const int rx = (kw - 1) * iterations / 2, ry = (kh - 1) * iterations / 2;
+    if (rx > D_MAXR || ry > D_MAXR) {
+        cvb_set_error("dilate: (k - 1) * iterations / 2 = %d x %d exceeds the supported radius %d", rx, ry, D_MAXR);
+        return CVB_ERR_INVALID;
+    }
+    dim3 grid((W + DT_W - 1) / DT_W, (H + DT_H - 1) / DT_H, n);
+    PROF(h, "k_dilate");
+    k_dilate<<<grid, 256, 0, h->stream>>>(src, H, W, rx, ry, dst);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
 
 int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh, uint8_t *edges)
 {

@@ -961,11 +961,11 @@ __global__ void __launch_bounds__(256) k_gaussian(const uint8_t *__restrict__ sr
         dst[(size_t)frame * H * W + (size_t)Y * W + X] = (uint8_t)((s + 32768u) >> 16);
     }
 }
-int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, uint8_t *dst)
+int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, double sigma, uint8_t *dst)
 {
     GaussK gk;
     memset(&gk, 0, sizeof gk);
-    if (cvb_host_gaussian_q8(ksize, gk.q) != CVB_OK) {
+    if (cvb_host_gaussian_q8_sigma(ksize, sigma, gk.q) != CVB_OK) {
         cvb_set_error("GaussianBlur ksize %d unsupported (odd, 1..31)", ksize);
         return CVB_ERR_INVALID;
     }

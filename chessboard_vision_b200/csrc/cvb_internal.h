@@ -40,6 +40,7 @@ struct CvbTables {
 const CvbTables &cvb_host_tables();
 void cvb_host_bilateral_tables(double sigma_color, double sigma_space, float *color768, float *space81);
 int  cvb_host_gaussian_q8(int ksize, int *q);
+int  cvb_host_gaussian_q8_sigma(int ksize, double sigma, int *q);
 int  cvb_host_get_perspective(const float *src, const float *dst, double *M);
 int  cvb_host_invert3(const double *a, double *t);
 void cvb_host_square_masks(int h, int w, uint8_t *mask);
@@ -141,7 +142,7 @@ int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame
 int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, const int32_t *minmax,
                      uint8_t *out);
 int launch_gray(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *gray);
-int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, uint8_t *dst);
+int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int ksize, double sigma, uint8_t *dst);
 // normalize (optional) + gray + blur5 + 256-bin histogram
 int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const int32_t *minmax,
                   uint8_t *enhanced, uint8_t *gray, uint8_t *blurred, int32_t *hist);
@@ -150,6 +151,7 @@ int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const i
 
 // ---- cvb_canny.cu -------------------------------------------------------------------------
 int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh, uint8_t *edges);
+int launch_dilate(cvb_handle *h, const uint8_t *src, int n, int H, int W, int kw, int kh, int iterations, uint8_t *dst);
 int launch_projections(cvb_handle *h, const uint8_t *plane, int n, int H, int W, uint32_t *rows, uint32_t *cols);
 
 // ---- cvb_grid.cu ----------------------------------------------------------------------

@@ -86,7 +86,9 @@ void cvb_host_bilateral_tables(double sigma_color, double sigma_space, float *co
 
 // cv2.getGaussianKernel(k, 0) quantised to Q8 with error diffusion, as the
 // u8 fixed-point GaussianBlur does (smooth.dispatch.cpp).
-int cvb_host_gaussian_q8(int k, int *q)
+int cvb_host_gaussian_q8(int k, int *q) { return cvb_host_gaussian_q8_sigma(k, 0.0, q); }
+// sigma > 0: cv2.GaussianBlur(src, (k, k), sigma) (board_detection.py:10 uses (7, 7), 1)
+int cvb_host_gaussian_q8_sigma(int k, double sigma_in, int *q)
 {
     if (k < 1 || k > 31 || !(k & 1)) return CVB_ERR_INVALID;
     double kern[31];
@@ -94,10 +96,10 @@ int cvb_host_gaussian_q8(int k, int *q)
                                        {0.25, 0.5, 0.25},
                                        {0.0625, 0.25, 0.375, 0.25, 0.0625},
                                        {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125}};
-    if (k <= 7) {
+    if (k <= 7 && sigma_in <= 0) {
         for (int i = 0; i < k; ++i) kern[i] = fixed[k / 2][i];
     } else {
-        double sigma = ((k - 1) * 0.5 - 1) * 0.3 + 0.8, s2 = -0.5 / (sigma * sigma), sum = 0;
+        double sigma = sigma_in > 0 ? sigma_in : ((k - 1) * 0.5 - 1) * 0.3 + 0.8, s2 = -0.5 / (sigma * sigma), sum = 0;
         for (int i = 0; i < k; ++i) {
             double x = i - (k - 1) * 0.5;
             kern[i] = std::exp(s2 * x * x);

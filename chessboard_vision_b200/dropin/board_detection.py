@@ -1,8 +1,10 @@
 """Drop-in for the reference's board_detection module: `warp_image`
 (board_detection.py:61-71) runs on the B200 (perspective matrix on the host in
 f64, resampling kernel on the device) and `reorder` (board_detection.py:49-58)
-is host index logic.  Every other name of the reference module (corner
-finding, grid drawing: calibration / GUI code outside the hot path) is
+is host index logic.  `find_chessboard_corners` (board_detection.py:4-27) runs its
+image part (gray, blur, Canny, dilation) on the B200 and the contour logic (a sequential
+border-following algorithm on the resulting mask) with host OpenCV, as the reference does.
+Every other name of the reference module (grid drawing: GUI code outside the hot path) is
 forwarded to the reference's own board_detection.py when it is on sys.path.
 """
 import numpy as np
@@ -22,6 +24,42 @@ def reorder(myPoints):
     out[1] = pts[np.argmin(d)]
     out[2] = pts[np.argmax(d)]
     return out
+
+
+def rectContour(contours):
+    """Contours with area > 100000 that simplify to four corners, largest first (board_detection.py:30-39)."""
+    import cv2
+    rect = []
+    for c in contours:
+        if cv2.contourArea(c) > 100000:
+            approx = cv2.approxPolyDP(c, 0.02 * cv2.arcLength(c, True), True)
+            if len(approx) == 4:
+                rect.append(c)
+    return sorted(rect, key=cv2.contourArea, reverse=True)
+
+
+def getCornerPoints(contour):
+    """board_detection.py:42-45"""
+    import cv2
+    return cv2.approxPolyDP(contour, 0.02 * cv2.arcLength(contour, True), True)
+
+
+def find_chessboard_corners(img, debug=False):
+    """board_detection.py:4-27 -> the four corners (TL, TR, BL, BR) of the largest four-sided contour,
+    or an empty array.  The mask comes from the GPU; `debug` (cv2.imshow in the reference) is ignored."""
+    import cv2
+    img = np.asarray(img)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("expected a uint8 HxWx3 BGR frame, got %s %r" % (img.dtype, img.shape))
+    mask = default_engine().contour_mask(np.ascontiguousarray(img))
+    contours, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    rect = rectContour(contours)
+    if len(rect) == 0:
+        return np.array([])
+    biggest = getCornerPoints(rect[0])
+    if biggest.size != 0:
+        return reorder(biggest)
+    return np.array([])
 
 
 def warp_image(img, points, display_size=(1280, 720), margin=100):

@@ -301,8 +301,20 @@ class Engine:
     def gray(self, img):
         return self._stage(self.lib.cvb_gray_dev, img, 3, 1)
 
-    def gaussian(self, plane, k=5):
+    def gaussian(self, plane, k=5, sigma=0.0):
+        """cv2.GaussianBlur(plane, (k, k), sigma) for u8 planes."""
+        if sigma and sigma > 0:
+            return self._stage(self.lib.cvb_gaussian_sigma_dev, plane, 1, 1, int(k), float(sigma))
         return self._stage(self.lib.cvb_gaussian_dev, plane, 1, 1, int(k))
+
+    def dilate(self, plane, kw=5, kh=5, iterations=1):
+        """cv2.dilate(plane, np.ones((kh, kw), np.uint8), iterations=iterations)"""
+        return self._stage(self.lib.cvb_dilate_dev, plane, 1, 1, int(kw), int(kh), int(iterations))
+
+    def contour_mask(self, img):
+        """The image part of board_detection.find_chessboard_corners (board_detection.py:9-14):
+        gray -> GaussianBlur(7x7, 1) -> Canny(30, 100) -> dilate(5x5, 3 iterations)."""
+        return self._stage(self.lib.cvb_contour_mask_dev, img, 3, 1)
 
     def normalize(self, img, return_minmax=False):
         a = np.asarray(img) if not isinstance(img, DevArray) else img

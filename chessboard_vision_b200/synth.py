@@ -97,3 +97,20 @@ def shape_atlas(seed=0, n_squares=48, min_side=8, max_side=128, plane_w=1024):
             img = sum(p[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)) / 9.0
         plane[y:y + h, x:x + w] = img.astype(np.uint8)
     return plane, rects
+
+
+def table_scene(H, W, seed=1):
+    """A bright board-sized quadrilateral (the calibration corners) on a darker table plus sensor noise:
+    the kind of frame board_detection.find_chessboard_corners is run on."""
+    rng = np.random.default_rng(seed)
+    tl, tr, bl, br = calib_points(H, W).astype(np.float64)
+    quad = [tl, tr, br, bl]
+    yy, xx = np.mgrid[:H, :W].astype(np.float64)
+    inside = np.ones((H, W), bool)
+    for a, b in zip(quad, quad[1:] + quad[:1]):
+        inside &= (b[0] - a[0]) * (yy - a[1]) - (b[1] - a[1]) * (xx - a[0]) >= 0
+    img = np.empty((H, W, 3), np.float32)
+    img[...] = (40, 50, 45)
+    img[inside] = (190, 200, 210)
+    img += rng.normal(0, 3, img.shape).astype(np.float32)
+    return np.clip(img, 0, 255).astype(np.uint8)

@@ -185,6 +185,17 @@ int cvb_warp_rot180_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
 int cvb_rotate_dev(cvb_handle *h, const uint8_t *src, int n, int H, int W, int C,
                    int rotate_code, uint8_t *dst);
 
+/* ---- board_detection.find_chessboard_corners, image part (calibration time) ---- */
+/* cv2.GaussianBlur(plane, (k, k), sigma) for u8; sigma <= 0: OpenCV's default for k   board_detection.py:10 */
+int cvb_gaussian_sigma_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
+                           int ksize, double sigma, uint8_t *out);
+/* cv2.dilate(plane, np.ones((kh, kw), np.uint8), iterations=iterations)               board_detection.py:13-14 */
+int cvb_dilate_dev(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
+                   int kw, int kh, int iterations, uint8_t *out);
+/* gray -> GaussianBlur(7x7, 1) -> Canny(30, 100) -> dilate(5x5, 3): the mask cv2.findContours
+ * is run on (host, control plane)                                                    board_detection.py:9-14 */
+int cvb_contour_mask_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, uint8_t *mask);
+
 /* ---- SmartGridExtractor.refine_grid building blocks (calibration time) -------- */
 /* cv2.Canny(gray, low, high) (aperture 3, L1 gradient)   grid_extractor.py:74 */
 int cvb_canny_dev(cvb_handle *h, const uint8_t *gray, int n, int H, int W,

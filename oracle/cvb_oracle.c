@@ -422,7 +422,10 @@ ORC_API void orc_gray(const u8 *bgr, int H, int W, long stride, u8 *dst)
 /*   getGaussianKernelFixedPoint_ED (Q8, error diffusion), fixedpoint.inl,  */
 /*   REFLECT_101 of the array being blurred                                 */
 /* ------------------------------------------------------------------------ */
-ORC_API int orc_gaussian_kernel_q8(int k, int *q)
+/* sigma <= 0: OpenCV's default for the size (fixed small kernels up to 7, else sigma from k) */
+ORC_API int orc_gaussian_kernel_q8_sigma(int k, double sigma, int *q);
+ORC_API int orc_gaussian_kernel_q8(int k, int *q) { return orc_gaussian_kernel_q8_sigma(k, 0.0, q); }
+ORC_API int orc_gaussian_kernel_q8_sigma(int k, double sigma_in, int *q)
 {
     if (k < 1 || k > 31 || (k & 1) == 0) return -1;
     double kern[31];
@@ -430,12 +433,12 @@ ORC_API int orc_gaussian_kernel_q8(int k, int *q)
     static const double t3[] = {0.25, 0.5, 0.25};
     static const double t5[] = {0.0625, 0.25, 0.375, 0.25, 0.0625};
     static const double t7[] = {0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125};
-    if (k == 1) memcpy(kern, t1, sizeof t1);
-    else if (k == 3) memcpy(kern, t3, sizeof t3);
-    else if (k == 5) memcpy(kern, t5, sizeof t5);
-    else if (k == 7) memcpy(kern, t7, sizeof t7);
+    if (sigma_in <= 0 && k == 1) memcpy(kern, t1, sizeof t1);
+    else if (sigma_in <= 0 && k == 3) memcpy(kern, t3, sizeof t3);
+    else if (sigma_in <= 0 && k == 5) memcpy(kern, t5, sizeof t5);
+    else if (sigma_in <= 0 && k == 7) memcpy(kern, t7, sizeof t7);
     else {
-        double sigma = ((k - 1) * 0.5 - 1) * 0.3 + 0.8;
+        double sigma = sigma_in > 0 ? sigma_in : ((k - 1) * 0.5 - 1) * 0.3 + 0.8;
         double scale2x = -0.5 / (sigma * sigma), sum = 0;
         for (int i = 0; i < k; i++) {
             double x = i - (k - 1) * 0.5;
@@ -456,10 +459,12 @@ ORC_API int orc_gaussian_kernel_q8(int k, int *q)
     return 0;
 }
 
-ORC_API int orc_gaussian(const u8 *src, int H, int W, long stride, int k, u8 *dst)
+ORC_API int orc_gaussian_sigma(const u8 *src, int H, int W, long stride, int k, double sigma, u8 *dst);
+ORC_API int orc_gaussian(const u8 *src, int H, int W, long stride, int k, u8 *dst) { return orc_gaussian_sigma(src, H, W, stride, k, 0.0, dst); }
+ORC_API int orc_gaussian_sigma(const u8 *src, int H, int W, long stride, int k, double sigma, u8 *dst)
 {
     int q[31];
-    if (orc_gaussian_kernel_q8(k, q)) return -1;
+    if (orc_gaussian_kernel_q8_sigma(k, sigma, q)) return -1;
     int r = k / 2;
     uint32_t *tmp = (uint32_t *)malloc(sizeof(uint32_t) * (long)H * W);
     for (int y = 0; y < H; y++)
@@ -1069,6 +1074,42 @@ ORC_API int orc_rotate(const u8 *src, int H, int W, int C, int code, u8 *dst)
             for (int c = 0; c < C; c++) dst[o * C + c] = src[((long)y * W + x) * C + c];
         }
     return 0;
+}
+
+/* cv2.dilate(src, np.ones((kh, kw)), iterations) (board_detection.py:13-14): a max filter; outside the image    */
+/* counts as -inf (morphologyDefaultBorderValue), so `iterations` passes of a kw x kh rectangle equal one pass of */
+/* ((kw-1)*iterations+1) x ((kh-1)*iterations+1).                                                              */
+ORC_API int orc_dilate(const u8 *src, int H, int W, int kw, int kh, int iterations, u8 *dst)
+{
+    if (kw < 1 || kh < 1 || !(kw & 1) || !(kh & 1) || iterations < 1) return -1;
+    const int rx = (kw - 1) * iterations / 2, ry = (kh - 1) * iterations / 2;
+    u8 *tmp = (u8 *)malloc((long)H * W);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int m = 0;
+            for (int xx = x - rx < 0 ? 0 : x - rx; xx <= x + rx && xx < W; xx++) if (src[(long)y * W + xx] > m) m = src[(long)y * W + xx];
+            tmp[(long)y * W + x] = (u8)m;
+        }
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            int m = 0;
+            for (int yy = y - ry < 0 ? 0 : y - ry; yy <= y + ry && yy < H; yy++) if (tmp[(long)yy * W + x] > m) m = tmp[(long)yy * W + x];
+            dst[(long)y * W + x] = (u8)m;
+        }
+    free(tmp);
+    return 0;
+}
+/* The image part of board_detection.find_chessboard_corners (board_detection.py:9-14):                       */
+/* gray -> GaussianBlur(7x7, sigma 1) -> Canny(30, 100) -> dilate(5x5, 3 iterations)                          */
+ORC_API void orc_contour_mask(const u8 *bgr, int H, int W, u8 *mask)
+{
+    const long n = (long)H * W;
+    u8 *g = (u8 *)malloc(n), *b = (u8 *)malloc(n), *e = (u8 *)malloc(n);
+    orc_gray(bgr, H, W, 3L * W, g);
+    orc_gaussian_sigma(g, H, W, W, 7, 1.0, b);
+    orc_canny(b, H, W, 30, 100, e);
+    orc_dilate(e, H, W, 5, 5, 3, mask);
+    free(g); free(b); free(e);
 }
 
 /* find_internal_lines (grid_extractor.py:83-110): border 0, seven window arg-max positions, border `length` */

@@ -149,11 +149,34 @@ def gray(bgr):
     return out
 
 
-def gaussian(g, k=5):
+def gaussian(g, k=5, sigma=0.0):
+    """cv2.GaussianBlur(g, (k, k), sigma) for u8 (sigma 0: OpenCV's default for the size)."""
     assert g.dtype == np.uint8 and g.ndim == 2 and (g.strides[1] == 1 or g.shape[1] == 1)
     H, W = g.shape; out = np.empty((H, W), np.uint8)
-    if lib().orc_gaussian(_p(g), C.c_int(H), C.c_int(W), C.c_long(g.strides[0]), C.c_int(k), _p(out)):
+    if lib().orc_gaussian_sigma(_p(g), C.c_int(H), C.c_int(W), C.c_long(g.strides[0]), C.c_int(k), C.c_double(sigma), _p(out)):
         raise ValueError("bad gaussian k=%r" % (k,))
+    return out
+
+
+def gaussian_kernel_q8_sigma(k, sigma):
+    q = np.zeros(31, np.int32)
+    if lib().orc_gaussian_kernel_q8_sigma(C.c_int(k), C.c_double(sigma), _p(q)):
+        raise ValueError("bad gaussian k=%r" % (k,))
+    return q[:k].copy()
+
+
+def dilate(plane, kw=5, kh=5, iterations=1):
+    """cv2.dilate(plane, np.ones((kh, kw), np.uint8), iterations=iterations)"""
+    g = _u8(plane); H, W = g.shape; out = np.empty_like(g)
+    if lib().orc_dilate(_p(g), C.c_int(H), C.c_int(W), C.c_int(kw), C.c_int(kh), C.c_int(iterations), _p(out)):
+        raise ValueError("bad dilate arguments")
+    return out
+
+
+def contour_mask(bgr):
+    """The image part of board_detection.find_chessboard_corners (board_detection.py:9-14)."""
+    bgr = _u8(bgr); H, W, _ = bgr.shape; out = np.empty((H, W), np.uint8)
+    lib().orc_contour_mask(_p(bgr), C.c_int(H), C.c_int(W), _p(out))
     return out
 
 

@@ -80,6 +80,16 @@ class FakeEngine:
     def get_perspective_transform(self, s, d):
         return O.get_perspective(s, d)
 
+    def gaussian(self, g, k=5, sigma=0.0):
+        return O.gaussian(np.ascontiguousarray(g), k, sigma)
+
+    def dilate(self, plane, kw=5, kh=5, iterations=1):
+        return O.dilate(plane, kw, kh, iterations)
+
+    def contour_mask(self, img):
+        FakeEngine.launches += 1
+        return O.contour_mask(img)
+
     def warp(self, img, M, size):
         return O.warp(img, M, size)
 

@@ -265,6 +265,24 @@ def main():
     rot["warp_small_rot180_sha"] = sha(w180)
     json.dump(rot, open(os.path.join(OUT, "rotate.json"), "w"), indent=1)
 
+    # ---- 11. find_chessboard_corners (calibration time; board_detection.py:4-27) --------------------
+    fc = {}
+    for (Hs, Ws, seed) in ((1080, 1920, 1), (720, 1280, 2), (1080, 1920, 3)):
+        im = synth.table_scene(Hs, Ws, seed)
+        g7 = cv2.GaussianBlur(cv2.cvtColor(im, cv2.COLOR_BGR2GRAY), (7, 7), 1)
+        mask = cv2.dilate(cv2.Canny(g7, 30, 100), np.ones((5, 5), np.uint8), iterations=3)
+        corners = bd.find_chessboard_corners(im)
+        fc["%dx%d_%d" % (Hs, Ws, seed)] = {"blur_sha": sha(g7), "mask_sha": sha(mask), "mask_px": int(np.count_nonzero(mask)),
+                                           "corners": corners.reshape(-1, 2).tolist() if corners.size else []}
+    plain = synth.board_frame(270, 480, 3)
+    fc["no_board_270x480"] = {"corners": bd.find_chessboard_corners(plain).reshape(-1, 2).tolist()}
+    small = synth.noise_frame(97, 133, 4)[:, :, 1].copy()
+    fc["blur_7_1_97x133"] = sha(cv2.GaussianBlur(small, (7, 7), 1))
+    fc["blur_9_2.5_97x133"] = sha(cv2.GaussianBlur(small, (9, 9), 2.5))
+    fc["dilate_5x5x3_97x133"] = sha(cv2.dilate(small, np.ones((5, 5), np.uint8), iterations=3))
+    fc["dilate_7x3x2_97x133"] = sha(cv2.dilate(small, np.ones((7, 3), np.uint8), iterations=2))
+    json.dump(fc, open(os.path.join(OUT, "find_corners.json"), "w"), indent=1)
+
     # ---- 6. warp on a small frame (full output) ---------------------------------------------------
     img = synth.noise_frame(270, 480, 9)
     pts = synth.calib_points(270, 480)
