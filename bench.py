@@ -442,7 +442,7 @@ def main():
         peak, peak_src = peaks()
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         # algorithmic bytes per frame per kernel
-        alg = {"k_tile_hist": 3 * npx, "k_fused": 6 * npx, "k_finish": 8 * npx, "k_threshold": 2 * npx,
+        alg = {"k_tile_hist": 6 * npx, "k_fused": 6 * npx, "k_finish": 8 * npx, "k_threshold": 2 * npx,
                "k_warp": 1012 * 916 * 3 + S * S * 3, "k_squares": S * S * 3 + 64 * 77 * 77 * (1 + 4 + 4 + 4 + 4 + 1),
                "k_clahe_lut": 64 * 256 * 5, "k_otsu": 1024}
         stages = {}

@@ -109,7 +109,7 @@ void cvb_destroy(cvb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
+    DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
                       &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks,
                       &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res};
@@ -336,14 +336,14 @@ int cvb_lab2bgr_dev(cvb_handle *h, const uint8_t *lab, int n, int H, int W, uint
 }
 
 static int clahe_tables(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W, const ClaheGeom &g,
-                        int32_t **hist_io, uint8_t **lut_io, int32_t *minmax_init)
+                        int32_t **hist_io, uint8_t **lut_io, int32_t *minmax_init, uint8_t *lab_out = nullptr)
 {
     const size_t nt = (size_t)g.tiles_x * g.tiles_y * n;
     int32_t *hist = *hist_io;
     uint8_t *lut = *lut_io;
     if (!hist) CVB_TRY(cvb_ws(h, h->ws_hist, nt * 256 * sizeof(int32_t), (void **)&hist));
     if (!lut) CVB_TRY(cvb_ws(h, h->ws_lut, nt * 256, (void **)&lut));
-    CVB_TRY(launch_tile_hist(h, src, from_bgr, n, H, W, g, hist, minmax_init));
+    CVB_TRY(launch_tile_hist(h, src, from_bgr, n, H, W, g, hist, minmax_init, lab_out));
     CVB_TRY(launch_clahe_lut(h, hist, n, g, lut));
     *hist_io = hist; *lut_io = lut;
     return CVB_OK;
@@ -471,9 +471,11 @@ int cvb_enhance_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, cons
     int32_t *hist = nullptr;
     uint8_t *lut = nullptr;
     // pass 1: tile histograms (+ min/max reset), LUTs
-    CVB_TRY(clahe_tables(h, bgr, 1, n, H, W, g, &hist, &lut, minmax));
+    // (the pass also stores the Lab pixels: pass 2 then skips RGB2Lab for every tile + halo pixel)
+    WS(ws_lab, uint8_t, fb * n, lab);
+    CVB_TRY(clahe_tables(h, bgr, 1, n, H, W, g, &hist, &lut, minmax, lab));
     // pass 2: lighting -> bilateral -> sharpen (+ min/max)
-    CVB_TRY(launch_fused(h, bgr, n, H, W, true, true, true, &g, lut, p->sigma_color, p->sigma_space, sharp, minmax));
+    CVB_TRY(launch_fused(h, lab, n, H, W, true, true, true, &g, lut, p->sigma_color, p->sigma_space, sharp, minmax, true));
     // pass 3/4: normalize -> gray -> blur -> Otsu -> mask
     if (!enhanced && !gray && !binary && !otsu_t) return CVB_OK;
     if (!gray && !binary && !otsu_t) return launch_normalize(h, sharp, n, (long)fb, minmax, enhanced);
@@ -916,6 +918,7 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const c
         CVB_TRY(cvb_ws(h, h->ws_enh, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_gray, npx * chunk, &t));
         CVB_TRY(cvb_ws(h, h->ws_bin, npx * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * chunk, &t));
         CVB_TRY(cvb_ws(h, h->ws_sharp, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_blur, npx * chunk, &t));
+        CVB_TRY(cvb_ws(h, h->ws_lab, fb * chunk, &t));
     }
     // the copy stream must not start before earlier work on the compute stream that reads ws_in is done
     CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[0], h->stream));

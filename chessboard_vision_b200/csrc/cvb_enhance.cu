@@ -186,23 +186,32 @@ CVB_DEV int l_of_bgr(const int (*tY)[256], const uint8_t *ltab, uint32_t b, uint
     return ltab[(tY[0][b] + tY[1][g] + tY[2][r] + 2048) >> 12];
 }
 
+// FROM_BGR && lab_out != nullptr: the pass also stores the whole Lab pixel (RGB2Lab_b, the same integers stage A of
+// k_fused would recompute for every tile + halo pixel), so that k_fused starts from Lab.
 template <bool FROM_BGR>
 __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ src, int H, int W, ClaheGeom g,
                                                    const CvbTables *__restrict__ tabs, int32_t *__restrict__ hist,
-                                                   int32_t *__restrict__ minmax_init)
+                                                   int32_t *__restrict__ minmax_init, uint8_t *__restrict__ lab_out)
 {
     __shared__ int s_hist[8][256];
     __shared__ int s_tY[3][256];          // per-channel contribution to the Y index numerator
     __shared__ uint8_t s_ltab[2048];
+    __shared__ uint16_t s_gam[FROM_BGR ? 256 : 1], s_cbrt[FROM_BGR ? 2048 : 1];   // for the Lab output
     const int tid = threadIdx.x, warp = tid >> 5;
     const int tile = blockIdx.x, tx = tile % g.tiles_x, ty = tile / g.tiles_x;
     const int frame = blockIdx.z;
+    const bool want_lab = FROM_BGR && lab_out != nullptr;
     for (int i = tid; i < 8 * 256; i += 256) (&s_hist[0][0])[i] = 0;
     if (FROM_BGR) {
         const int gv = tabs->gamma[tid];
         s_tY[0][tid] = gv * 296; s_tY[1][tid] = gv * 2929; s_tY[2][tid] = gv * 871;
         for (int i = tid; i < 2048 / 4; i += 256)
             reinterpret_cast<uint32_t *>(s_ltab)[i] = reinterpret_cast<const uint32_t *>(tabs->ltab)[i];
+        if (want_lab) {
+            s_gam[tid] = (uint16_t)gv;
+            for (int i = tid; i < 2048 / 2; i += 256)
+                reinterpret_cast<uint32_t *>(s_cbrt)[i] = reinterpret_cast<const uint32_t *>(tabs->cbrt)[i];
+        }
     }
     if (minmax_init && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         minmax_init[2 * frame] = 255; minmax_init[2 * frame + 1] = 0;
@@ -212,10 +221,24 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
     const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, g.tile_h);
     constexpr int CH = FROM_BGR ? 3 : 1;
     const uint8_t *img = src + (size_t)frame * H * W * CH;
+    uint8_t *lab = want_lab ? lab_out + (size_t)frame * H * W * 3 : nullptr;
     int *my = s_hist[warp];
+    // one pixel: histogram of L; with want_lab the packed (L, a, b) word is returned as well
+    auto lab_px = [&](uint32_t b, uint32_t gch, uint32_t r) -> uint32_t {
+        const int Bl = s_gam[b], Gl = s_gam[gch], Rl = s_gam[r];
+        const int fX = s_cbrt[(Rl * 1777 + Gl * 1541 + Bl * 778 + 2048) >> 12];
+        const int fY = s_cbrt[(Rl * 871 + Gl * 2929 + Bl * 296 + 2048) >> 12];
+        const int fZ = s_cbrt[(Rl * 73 + Gl * 448 + Bl * 3575 + 2048) >> 12];
+        const int L = (296 * fY - 1336934 + 16384) >> 15;                    // never saturate (tests/test_abi.py)
+        const int A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+        const int Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+        atomicAdd(&my[L], 1);
+        return pack_bgr(L, A, Bc);
+    };
     const int x_lo = tx * g.tile_w, y_lo = ty * g.tile_h + r0;
     const bool inside = x_lo + g.tile_w <= W && ty * g.tile_h + r1 <= H;
-    const bool fast = inside && (g.tile_w % 16 == 0) && (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool fast = inside && (g.tile_w % 16 == 0) && (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                      (!want_lab || (reinterpret_cast<uintptr_t>(lab_out) & 15) == 0);
     if (fast) {
         const int gpr = g.tile_w >> 4;                       // 16-pixel groups per tile row
         const int ngroups = (r1 - r0) * gpr;
@@ -226,13 +249,29 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
                 const uint4 *p = reinterpret_cast<const uint4 *>(img + px * 3);
                 const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
                 const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                if (want_lab) {
+                    uint32_t o[12];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {       // 4 pixels per 3 words: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-                    const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
-                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff)], 1);
-                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff)], 1);
-                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff)], 1);
-                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24)], 1);
+                    for (int k = 0; k < 4; ++k) {       // 4 pixels per 3 words: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
+                        const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+                        const uint32_t q0 = lab_px(w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff);
+                        const uint32_t q1 = lab_px(w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff);
+                        const uint32_t q2 = lab_px((w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff);
+                        const uint32_t q3 = lab_px((w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24);
+                        o[3 * k] = q0 | (q1 << 24); o[3 * k + 1] = (q1 >> 8) | (q2 << 16); o[3 * k + 2] = (q2 >> 16) | (q3 << 8);
+                    }
+                    uint4 *op = reinterpret_cast<uint4 *>(lab + px * 3);
+                    op[0] = make_uint4(o[0], o[1], o[2], o[3]); op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    op[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t w0 = w[3 * k], w1 = w[3 * k + 1], w2 = w[3 * k + 2];
+                        atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 & 0xff, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff)], 1);
+                        atomicAdd(&my[l_of_bgr(s_tY, s_ltab, w0 >> 24, w1 & 0xff, (w1 >> 8) & 0xff)], 1);
+                        atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w1 >> 16) & 0xff, w1 >> 24, w2 & 0xff)], 1);
+                        atomicAdd(&my[l_of_bgr(s_tY, s_ltab, (w2 >> 8) & 0xff, (w2 >> 16) & 0xff, w2 >> 24)], 1);
+                    }
                 }
             } else {
                 const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img + px));
@@ -249,14 +288,19 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
         for (int i = tid; i < npx; i += 256) {
             const int ry = i / g.tile_w, rx = i - ry * g.tile_w;
             const int sy = reflect101(y_lo + ry, H), sx = reflect101(x_lo + rx, W);
-            int L;
             if (FROM_BGR) {
                 const uint8_t *p = img + ((size_t)sy * W + sx) * 3;
-                L = l_of_bgr(s_tY, s_ltab, p[0], p[1], p[2]);
+                if (want_lab) {
+                    // mirrored positions of the padded tile grid store their source pixel again: same value
+                    const uint32_t q = lab_px(p[0], p[1], p[2]);
+                    uint8_t *o = lab + ((size_t)sy * W + sx) * 3;
+                    o[0] = (uint8_t)q; o[1] = (uint8_t)(q >> 8); o[2] = (uint8_t)(q >> 16);
+                } else {
+                    atomicAdd(&my[l_of_bgr(s_tY, s_ltab, p[0], p[1], p[2])], 1);
+                }
             } else {
-                L = img[(size_t)sy * W + sx];
+                atomicAdd(&my[img[(size_t)sy * W + sx]], 1);
             }
-            atomicAdd(&my[L], 1);
         }
     }
     __syncthreads();
@@ -265,8 +309,9 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
     for (int w = 0; w < 8; ++w) tot += s_hist[w][tid];
     if (tot) atomicAdd(&hist[((size_t)frame * g.tiles_x * g.tiles_y + tile) * 256 + tid], tot);
 }
+
 int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W, const ClaheGeom &g,
-                     int32_t *hist, int32_t *minmax_init)
+                     int32_t *hist, int32_t *minmax_init, uint8_t *lab_out)
 {
     const int tiles = g.tiles_x * g.tiles_y;
     CVB_CHECK_CUDA(cudaMemsetAsync(hist, 0, sizeof(int32_t) * 256 * tiles * (size_t)n, h->stream));
@@ -275,8 +320,8 @@ int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int
     splits = max(1, min(splits, (g.tile_h + 7) / 8));
     dim3 grid(tiles, splits, n);
     PROF(h, "k_tile_hist");
-    if (from_bgr) k_tile_hist<true><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
-    else k_tile_hist<false><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init);
+    if (from_bgr) k_tile_hist<true><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init, lab_out);
+    else k_tile_hist<false><<<grid, 256, 0, h->stream>>>(src, H, W, g, h->d_tables, hist, minmax_init, nullptr);
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
@@ -377,6 +422,7 @@ struct FusedArgs {
     const float *wlut;        // [10][768] space*colour weights, or [768] colour weights when !FOLD (device)
     float sw[81];             // spatial weights [dy+4][dx+4] (used when !FOLD)
     int32_t *minmax;          // per frame {min,max} or null
+    int src_is_lab;           // LIGHT: src already holds (L, a, b) bytes (stored by the tile-histogram pass)
 };
 
 // class of a tap by squared radius: 0,1,2,4,5,8,9,10,13,16 -> 0..9
@@ -495,7 +541,8 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
             uint32_t q;
             if (LIGHT) {
                 int L, A, B;
-                bgr2lab_px(sTab, c0, c1, c2, L, A, B);
+                if (a.src_is_lab) { L = c0; A = c1; B = c2; }
+                else bgr2lab_px(sTab, c0, c1, c2, L, A, B);
                 const uint32_t o1 = cy.t1 + (uint32_t)L, o2 = cy.t2 + (uint32_t)L;
                 const float l11 = (float)__ldg(lut + (o1 + cx.t1)), l12 = (float)__ldg(lut + (o1 + cx.t2));
                 const float l21 = (float)__ldg(lut + (o2 + cx.t1)), l22 = (float)__ldg(lut + (o2 + cx.t2));
@@ -784,9 +831,10 @@ static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 
 int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool light, bool bilateral, bool sharpen,
                  const ClaheGeom *g, const uint8_t *lut, double sigma_color, double sigma_space, uint8_t *out,
-                 int32_t *minmax)
+                 int32_t *minmax, bool src_is_lab)
 {
     FusedArgs a;
+    a.src_is_lab = src_is_lab ? 1 : 0;
     a.src = src; a.dst = out; a.H = H; a.W = W; a.tabs = h->d_tables; a.lut = lut; a.minmax = minmax;
     a.wlut = nullptr;
     if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
@@ -831,7 +879,7 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
 int launch_correct_lighting(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const ClaheGeom &g,
                             const uint8_t *lut, uint8_t *out)
 {
-    return launch_fused(h, bgr, n, H, W, true, false, false, &g, lut, 0, 0, out, nullptr);
+    return launch_fused(h, bgr, n, H, W, true, false, false, &g, lut, 0, 0, out, nullptr, false);
 }
 
 // ---------------------------------------------------------------------------------------

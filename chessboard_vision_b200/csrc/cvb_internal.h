@@ -79,7 +79,7 @@ struct cvb_handle {
     float *d_color = nullptr;
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
-    DevBuf ws_prof, ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
+    DevBuf ws_lab, ws_prof, ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
     DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
     cudaStream_t copy_stream = nullptr;
@@ -127,8 +127,9 @@ int launch_color_profile(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
 int launch_bgr2lab(cvb_handle *h, const uint8_t *bgr, long npx, uint8_t *lab);
 int launch_lab2bgr(cvb_handle *h, const uint8_t *lab, long npx, uint8_t *bgr);
 // histogram of L (from_bgr=1: src is BGR, L computed on the fly) or of a u8 plane
+// lab_out (from_bgr only, may be null): the Lab pixels of the frames, for launch_fused(..., src_is_lab = true)
 int launch_tile_hist(cvb_handle *h, const uint8_t *src, int from_bgr, int n, int H, int W,
-                     const ClaheGeom &g, int32_t *hist, int32_t *minmax_init);
+                     const ClaheGeom &g, int32_t *hist, int32_t *minmax_init, uint8_t *lab_out);
 int launch_clahe_lut(cvb_handle *h, const int32_t *hist, int n, const ClaheGeom &g, uint8_t *lut);
 int launch_clahe_apply_plane(cvb_handle *h, const uint8_t *src, int n, int H, int W, const ClaheGeom &g,
                              const uint8_t *lut, uint8_t *dst);
@@ -137,7 +138,7 @@ int launch_correct_lighting(cvb_handle *h, const uint8_t *bgr, int n, int H, int
 // the fused tile kernel: [lighting] -> [bilateral] -> [sharpen] (+ min/max)
 int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool light, bool bilateral, bool sharpen,
                  const ClaheGeom *g, const uint8_t *lut, double sigma_color, double sigma_space,
-                 uint8_t *out, int32_t *minmax);
+                 uint8_t *out, int32_t *minmax, bool src_is_lab = false);
 int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, int32_t *minmax);
 int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, const int32_t *minmax,
                      uint8_t *out);
