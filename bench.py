@@ -396,6 +396,27 @@ def main():
         extras["config3_change_stats_64_pairs"] = {"ms_per_batch": ms3, "frames_per_s": nb / ms3 * 1e3,
                                                    "what": "warp + 64 squares: absdiff delta, moments, centre/border, rings, "
                                                            "z-score detect + EMA update (resident inputs)"}
+        # config 4 shape: 8 concurrent 3840x2160 camera streams on this GPU (64 streams over 8 GPUs), one frame each per step
+        n4, H4, W4 = 8, 2160, 3840
+        f4 = np.stack([synth.board_frame(H4, W4, 40 + i) for i in range(2)])
+        d4 = eng.upload(np.stack([f4[i % 2] for i in range(n4)]))
+        M4 = eng.get_perspective_transform(synth.calib_points(H4, W4), [[0, 0], [S, 0], [0, S], [S, S]])
+        st4 = eng.new_state(n4, S, S); s4 = eng.empty((n4, len(rects)), STATS_DTYPE); o4 = eng.empty((n4,), np.int32)
+        eng.pipeline_dev(d4, M4, rects, pp_cal, st4, stats=s4, otsu_t=o4)
+        for _ in range(2):
+            eng.pipeline_dev(d4, M4, rects, pp, st4, stats=s4, otsu_t=o4)
+        e0, e1 = eng.event(), eng.event()
+        eng.record(e0)
+        for _ in range(5):
+            eng.pipeline_dev(d4, M4, rects, pp, st4, stats=s4, otsu_t=o4)
+        eng.record(e1)
+        ms4 = eng.elapsed_ms(e0, e1) / 5
+        extras["config4_8_streams_4k"] = {"ms_per_step": ms4, "frames_per_s": n4 / ms4 * 1e3,
+                                          "mpixels_per_s": n4 * H4 * W4 / ms4 / 1e3,
+                                          "what": "8 resident 3840x2160 streams per GPU, full path with per-stream state"}
+        for x in (d4, s4, o4):
+            x.free()
+        st4.free()
         # "next" row: Hough circles on the 64 gray+blur squares of warped boards with pieces (k_hough),
         # beside the reference's cv2.HoughCircles loop on this box's host cores
         nh = 64
