@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(HNT, 4) k_hough(const uint8_t *__restrict__ pl
     uint16_t *c_idx = reinterpret_cast<uint16_t *>(smem + L.off_union + 4 * maxc);
     uint16_t *c_sup = c_idx + maxc;
 
-    if (tid == 0) { M.nnz = 0; M.ncent = 0; M.kept = 0; }
+    if (tid == 0) { M.nnz = 0; M.ncent = 0; M.kept = 0; M.pad = 0; }
     for (int i = tid; i < ncells; i += HNT) acc[i] = 0;
     // ---- A: gray with a replicated border; Canny ----
     const uint8_t *img = planes + (size_t)frame * plane_stride + (size_t)S.y * PW + S.x;
@@ -131,10 +131,23 @@ __global__ void __launch_bounds__(HNT, 4) k_hough(const uint8_t *__restrict__ pl
         s_map[i] = v;
     }
     __syncthreads();
-    // hysteresis: grow the strong set through weak candidates until nothing changes
+    // hysteresis: grow the strong set through weak candidates until nothing changes.  Only the weak candidates can
+    // change, so they are listed once (in the edge-list buffer, not yet in use) and the sweeps walk that list.
+    for (int i0 = 0; i0 < npad; i0 += HNT) {
+        const int i = i0 + tid;
+        const bool weak = i < npad && s_map[i] == 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, weak);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&M.pad, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (weak) nz[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)i;
+    }
+    __syncthreads();
+    const int nweak = M.pad;
     for (;;) {
         bool mine = false;
-        for (int i = tid; i < npad; i += HNT) {
+        for (int e = tid; e < nweak; e += HNT) {
+            const int i = nz[e];
             if (s_map[i] == 0) {
                 const bool hit = s_map[i - gp - 1] == 2 || s_map[i - gp] == 2 || s_map[i - gp + 1] == 2 || s_map[i - 1] == 2 ||
                                  s_map[i + 1] == 2 || s_map[i + gp - 1] == 2 || s_map[i + gp] == 2 || s_map[i + gp + 1] == 2;
