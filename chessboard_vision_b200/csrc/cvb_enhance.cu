@@ -1038,7 +1038,7 @@ int launch_gaussian(cvb_handle *h, const uint8_t *src, int n, int H, int W, int 
 // straddles the right image edge; the generic instance keeps the byte paths.
 // ---------------------------------------------------------------------------------------
 template <bool NORM, bool FAST>
-__global__ void __launch_bounds__(256) k_finish(const uint8_t *__restrict__ src, int H, int W,
+__global__ void __launch_bounds__(256, 6) k_finish(const uint8_t *__restrict__ src, int H, int W,
                                                 const int32_t *__restrict__ minmax, uint8_t *__restrict__ enhanced,
                                                 uint8_t *__restrict__ gray, uint8_t *__restrict__ blurred,
                                                 int32_t *__restrict__ hist)
