@@ -482,9 +482,10 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": d["frac_of_hbm_peak"], "traffic": d["traffic_bytes_per_launch"],
                     "traffic_source": traffic.get("source"), "peak_source": peak_src,
-                    "note": "k_fused is bound by the FP32/LSU pipes (49-tap bilateral, ~700 ops per pixel), not by HBM; "
-                            "its HBM fraction is reported as the contract asks, the per-stage table gives the streaming "
-                            "kernels' fractions", "stages": stages}
+                    "note": "k_fused is bound by the shared-memory (LSU) pipe and issue slots, not by HBM: 49 bilateral taps "
+                            "per pixel, each a weight-table lookup that averages 2.5 shared-memory wavefronts, ~670 "
+                            "instructions per pixel (profiles/r01_notes.md); its HBM fraction is reported as the contract "
+                            "asks, the per-stage table gives the streaming kernels' fractions", "stages": stages}
         fp32_ops = 49 * 8 * npx * n       # 49 taps x (vabsdiff, LUT load, mul, add, 3 fma, convert) per pixel, lower bound
         roofline["fp32_pipe"] = {"ops_per_launch_lower_bound": fp32_ops,
                                  "achieved_tops": fp32_ops / (stages["k_fused"]["ms_per_launch"] / 1e3) / 1e12
