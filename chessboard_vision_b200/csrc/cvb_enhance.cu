@@ -867,7 +867,15 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     // sharpen halo the bilateral stage then has 31 runs x 33 row pairs = 1023 work items for its two rounds of 512
     // threads, the sharpen stage exactly 15 pixels per thread; two CTAs fit an SM because the colour tables share
     // memory with the B tile.  The folded 30 KB weight table beat the 3 KB one.
-    if (light && bilateral && sharpen) return launch_fused_t<120, 64, true, true, true, 512, 1, 2>(h, a, n);
+    if (light && bilateral && sharpen) {
+        // CVB_FUSED=<variant> routes the process_pipeline path through the persistent TMA-fed kernel of cvb_fused2.cu
+        // (needs Lab rows with a 16-byte pitch); unset = this file's per-tile kernel, which is still the faster one
+        // (profiles/r02_notes.md)
+        static const char *env = getenv("CVB_FUSED");
+        if (env && env[0] >= '0' && env[0] <= '9' && src_is_lab && minmax && fused_tma_applicable(H, W, src, out))
+            return launch_fused_tma(h, src, n, H, W, *g, lut, h->d_color, a.sw, out, minmax, atoi(env));
+        return launch_fused_t<120, 64, true, true, true, 512, 1, 2>(h, a, n);
+    }
     if (!light && bilateral && !sharpen) return launch_fused_t<120, 64, false, true, false, 512, 1, 2>(h, a, n);
     if (!light && bilateral && sharpen) return launch_fused_t<120, 64, false, true, true, 512, 1, 2>(h, a, n);
     if (light && bilateral && !sharpen) return launch_fused_t<120, 64, true, true, false, 512, 1, 2>(h, a, n);

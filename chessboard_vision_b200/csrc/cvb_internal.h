@@ -139,6 +139,10 @@ int launch_correct_lighting(cvb_handle *h, const uint8_t *bgr, int n, int H, int
 int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool light, bool bilateral, bool sharpen,
                  const ClaheGeom *g, const uint8_t *lut, double sigma_color, double sigma_space,
                  uint8_t *out, int32_t *minmax, bool src_is_lab = false);
+// cvb_fused2.cu: the same three stages as one persistent kernel fed by tensor-map TMA loads of the Lab tiles
+bool fused_tma_applicable(int H, int W, const uint8_t *lab, const uint8_t *out);
+int launch_fused_tma(cvb_handle *h, const uint8_t *lab, int n, int H, int W, const ClaheGeom &g, const uint8_t *lut,
+                     const float *d_wlut, const float *space81, uint8_t *out, int32_t *minmax, int variant);
 int launch_minmax(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, int32_t *minmax);
 int launch_normalize(cvb_handle *h, const uint8_t *src, int n, long bytes_per_frame, const int32_t *minmax,
                      uint8_t *out);

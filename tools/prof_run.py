@@ -40,7 +40,9 @@ if os.environ.get("CVB_HOUGH"):
 print("total %.3f ms/step  -> %.0f frames/s" % (tot / steps, n * steps / tot * 1e3))
 if os.environ.get("CVB_CHECK"):
     import oracle as O
-    for shp in ((270, 480), (133, 251)):
-        f = synth.board_frame(*shp, 3)
-        ok = np.array_equal(eng.process_pipeline(f), O.process_pipeline(f, True))
-        print("parity", shp, "OK" if ok else "MISMATCH")
+    for shp in ((270, 480), (133, 251), (480, 640), (64, 128), (16, 16), (200, 256), (720, 1280), (1080, 1920)):
+        for kind in ("board", "noise"):
+            f = synth.frame_batch(1, shp[0], shp[1], kind, 3)[0]
+            got, ref = eng.process_pipeline(f), O.process_pipeline(f, True)
+            bad = int((got != ref).sum())
+            print("parity", shp, kind, "OK" if bad == 0 else "MISMATCH %d values, first at %s" % (bad, np.argwhere(got != ref)[0]))
