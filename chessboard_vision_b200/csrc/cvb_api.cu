@@ -56,7 +56,13 @@ static void prof_clear(cvb_handle *h)
     type *var = nullptr;          \
     CVB_TRY(cvb_ws(h, h->buf, sizeof(type) * (size_t)(count), (void **)&var))
 
-#define REQ_H(h) CVB_REQUIRE((h) != nullptr, "null handle")
+// every public entry point runs on the handle's own device, whatever device the calling thread had current
+// (several engines, one per GPU, may live in one process)
+#define REQ_H(h)                                         \
+    do {                                                 \
+        CVB_REQUIRE((h) != nullptr, "null handle");      \
+        CVB_CHECK_CUDA(cudaSetDevice((h)->device));      \
+    } while (0)
 #define REQ_IMG(n, H, W)                                                                                      \
     CVB_REQUIRE((n) >= 1 && (n) <= 65535 && (H) >= 1 && (W) >= 1 && (H) <= 32768 && (W) <= 32768,              \
                 "bad batch/shape n=%d H=%d W=%d", (n), (H), (W))
@@ -622,7 +628,7 @@ int cvb_state_create(cvb_handle *h, int n_streams, int BH, int BW, cvb_state **o
 void cvb_state_destroy(cvb_state *s)
 {
     if (!s) return;
-    if (s->h) cudaStreamSynchronize(s->h->stream);
+    if (s->h) { cudaSetDevice(s->h->device); cudaStreamSynchronize(s->h->stream); }
     cudaFree(s->pd_ref); cudaFree(s->pd_cur); cudaFree(s->flags); cudaFree(s->cd_mean); cudaFree(s->cd_var);
     delete s;
 }
@@ -797,7 +803,10 @@ static int hough_impl(cvb_handle *h, const uint8_t *planes, int n, int PH, int P
         CVB_REQUIRE(rects[i].w >= 1 && rects[i].h >= 1 && rects[i].x >= 0 && rects[i].y >= 0 &&
                         rects[i].x + rects[i].w <= PW && rects[i].y + rects[i].h <= PH,
                     "square %d (%d,%d %dx%d) outside the %dx%d plane", i, rects[i].x, rects[i].y, rects[i].w, rects[i].h, PW, PH);
-        CVB_REQUIRE(rects[i].w <= CVB_HOUGH_MAX_DIM && rects[i].h <= CVB_HOUGH_MAX_DIM,
+        bool used = select == nullptr;
+        for (int f = 0; f < n && !used; ++f) used = select[(size_t)f * n_sq + i] != 0;
+        // the size limit only concerns squares some frame selects (an unselected large rectangle is harmless)
+        CVB_REQUIRE(!used || (rects[i].w <= CVB_HOUGH_MAX_DIM && rects[i].h <= CVB_HOUGH_MAX_DIM),
                     "square %d is %dx%d: the Hough kernel handles squares up to %d pixels a side", i, rects[i].w, rects[i].h,
                     CVB_HOUGH_MAX_DIM);
     }

@@ -183,9 +183,10 @@ int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double
     PROF(h, "k_canny_nms");
     k_canny_nms<<<grid, 256, 0, h->stream>>>(gray, H, W, low, high, map);
     LAUNCH_CHECK(h);
-    // sweeps until no tile changes; a chain has to cross at most (tiles in x + tiles in y) tile borders per ... bounded anyway
-    const int max_sweeps = 4 * (int)(grid.x + grid.y) + 8;
-    for (int it = 0; it < max_sweeps; ++it) {
+    // Sweeps until no tile changes.  A sweep floods inside every 32-px tile, so a weak chain advances by at least one
+    // tile border per sweep; the map only ever moves 0 -> 2, hence the loop terminates (a serpentine chain can need about
+    // tiles_x * tiles_y sweeps, far more than any fixed small cap -- cv2.Canny follows it to the end, so do we).
+    for (;;) {
         CVB_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
         PROF(h, "k_canny_hyst");
         k_canny_hyst<<<grid, 256, 0, h->stream>>>(map, H, W, flag);

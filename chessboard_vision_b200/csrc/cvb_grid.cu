@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, CVB_SQ_MINB) k_squares(const SquareArgs a
     const bool state = a.flags != nullptr;
     const int fl0 = state ? a.flags[first] : 0;
     const bool has_ref = (fl0 & 1) != 0;
-    const bool has_cd = (fl0 & 2) != 0;
+    const bool has_cd = (fl0 & 6) == 6;         // bit 1: a mean is stored, bit 2: a variance is stored
 
     const bool need_pd = (ops & (CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF)) != 0;
     const bool need_cd = (ops & (CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE)) != 0 && selected && state;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256, CVB_SQ_MINB) k_squares(const SquareArgs a
             if (!ok[j]) continue;
             const unsigned o = ofs[j];
             const float gf = (float)gv[j];
-            if (calib) { cd_mean[o] = m[j]; cd_var[o] = v[j]; flags[o] |= 2; }
+            if (calib) { cd_mean[o] = m[j]; cd_var[o] = v[j]; flags[o] |= 6; }
             if (ops & CVB_SQ_CD_DETECT) {
                 const float z = __fdiv_rn(fabsf(__fsub_rn(gf, m[j])), __fsqrt_rn(v[j]));
                 if (z > zthr) ++cd_cnt;

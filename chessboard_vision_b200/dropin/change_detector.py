@@ -30,7 +30,7 @@ class ChangeDetectorB200:
         self._e = default_engine(device)
         self._run = SquareRunner(self._e)
         self.means = self._run.bind(_lib.PLANE_CD_MEAN, np.float32, 2)
-        self.variances = self._run.bind(_lib.PLANE_CD_VAR, np.float32, 2)
+        self.variances = self._run.bind(_lib.PLANE_CD_VAR, np.float32, 4)
         self.is_calibrated = False
         self.focus_squares = set()
         self.piece_detector = PieceDetector()
@@ -81,6 +81,9 @@ class ChangeDetectorB200:
         sel = [k for k in squares if k in self.focus_squares] if self.focus_squares else None
         if sel is not None and not sel:
             return
+        for pos in (sel if sel is not None else squares):
+            if pos not in self.means or pos not in self.variances:
+                raise KeyError(pos)            # the reference indexes self.means[pos] (change_detector.py:81)
         self._launch(squares, SQ_CD_UPDATE, select_keys=sel)
 
     def detect_changes(self, squares):
@@ -99,6 +102,7 @@ class ChangeDetectorB200:
             return results
         stats, _ = self._launch(squares, SQ_CD_DETECT, select_keys=to_check if self.focus_squares else None,
                                 want_stats=True)
+        hits = []
         for pos in to_check:
             st = stats[pos]
             if not st["cd_valid"]:
@@ -107,8 +111,14 @@ class ChangeDetectorB200:
             if pct_changed < 5.0:
                 continue
             intensity = 'TOTAL' if pct_changed > 75 else 'PARCIAL' if pct_changed > 15 else 'LEVE'
-            pd_result = self.piece_detector.detect_piece(squares[pos], pos)
-            results[pos] = {'z_score': float(st["cd_zmax"]), 'pct_changed': pct_changed, 'intensity': intensity,
+            hits.append((pos, float(st["cd_zmax"]), pct_changed, intensity))
+        # change_detector.py:156 asks the piece detector about every reported square; here all of them go through one
+        # statistics launch and one Hough launch (a replaced piece_detector without the batch method is called per square)
+        batch = getattr(self.piece_detector, 'detect_pieces', None)
+        pieces = batch(squares, [h[0] for h in hits]) if (hits and callable(batch)) else None
+        for pos, zmax, pct_changed, intensity in hits:
+            pd_result = pieces[pos] if isinstance(pieces, dict) and pos in pieces else self.piece_detector.detect_piece(squares[pos], pos)
+            results[pos] = {'z_score': zmax, 'pct_changed': pct_changed, 'intensity': intensity,
                             'is_circular': pd_result['has_piece'], 'center_ratio': 1.0}
         return results
 

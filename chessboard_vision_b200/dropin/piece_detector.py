@@ -219,6 +219,17 @@ class PieceDetector:
         st, gray = self._one(square_img)
         return self._detect_from(st, gray)
 
+    def detect_pieces(self, squares_dict, positions):
+        """`detect_piece` (piece_detector.py:272-346) for several squares of one board at once: ONE statistics launch
+        and ONE Hough launch instead of two launches and a device-to-host read per square.  No reference, cache or
+        history is touched, exactly like a sequence of detect_piece calls.  -> {pos: result}"""
+        positions = [p for p in positions if p in squares_dict]
+        if not positions:
+            return {}
+        stats = self._stats(squares_dict)
+        circles = self._hough_batch(stats, positions)
+        return {pos: self._detect_from(stats[pos], self._shape_of(pos), circles.get(pos)) for pos in positions}
+
     def detect_all_pieces(self, squares_dict, use_smoothing=True, use_delta=True, squares_to_check=None):
         """piece_detector.py:348-440 -> (results, visual_changes); one kernel launch for the 64 squares."""
         results, visual_changes, to_update = {}, set(), []

@@ -11,6 +11,7 @@ ChangeDetector / PieceDetector compute through cv2 + numpy
 change_detector.py:36-167, piece_detector.py:82-207).
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -159,9 +160,30 @@ def _rect_array(rects):
     return arr
 
 
+class _LockedLib:
+    """The C library behind one lock per engine.  A cvb_handle is not re-entrant (its workspaces and staging caches
+    are unsynchronised) and ctypes releases the GIL during a call, so two Python threads sharing an engine -- the
+    reference application has a second thread (lichess_session.py:36) -- must not be inside the library at once."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock, self._cache = lib, lock, {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw, lock = getattr(self._lib, name), self._lock
+
+            def fn(*args):
+                with lock:
+                    return raw(*args)
+            self._cache[name] = fn
+        return fn
+
+
 class Engine:
     def __init__(self, device=0):
-        self.lib = _lib.load()
+        self.lock = threading.RLock()
+        self.lib = _LockedLib(_lib.load(), self.lock)
         self.h = None
         h = C.c_void_p()
         check(self.lib.cvb_create(int(device), C.byref(h)))

@@ -7,6 +7,12 @@ the arrays live on the GPU as planes shaped like the board image (each square
 owns its rectangle); `PlaneDict` is the dict-like window onto one plane:
 reads download the plane lazily, writes are staged and flushed before the
 next kernel launch.
+
+Reading `d[key]` hands out ONE host array per key until the device rewrites the
+plane: in-place edits of it (`d[key][...] = x`, `d[key] *= k`, which the
+reference's plain dicts allow) are noticed at the next launch and uploaded.
+After a kernel that rewrites the plane the entry is a new array, exactly as the
+reference rebinds `self.means[pos] = new_mean` (change_detector.py:91-92).
 """
 from collections.abc import MutableMapping
 
@@ -24,6 +30,7 @@ class PlaneDict(MutableMapping):
         self._removed = False       # a key was deleted since the last flush
         self._hostonly = {}         # values whose key / shape is not part of the current board layout
         self._host = None           # downloaded copy of the device plane
+        self._live = {}             # key -> (array handed to the caller, pristine copy) since the last device write
 
     # -- Mapping protocol --
     def __getitem__(self, key):
@@ -38,11 +45,15 @@ class PlaneDict(MutableMapping):
             raise KeyError(key)
         if self._host is None:
             self._host = self._r.state.get(0, self._plane)
-        x, y, w, h = rect
-        return self._host[y:y + h, x:x + w].copy()
+        if key not in self._live:
+            x, y, w, h = rect
+            arr = self._host[y:y + h, x:x + w].copy()
+            self._live[key] = (arr, arr.copy())
+        return self._live[key][0]
 
     def __setitem__(self, key, value):
         self._staged[key] = np.array(value, dtype=self._dtype)
+        self._live.pop(key, None)
         self._hostonly.pop(key, None)
         self._present.add(key)
 
@@ -51,6 +62,7 @@ class PlaneDict(MutableMapping):
             raise KeyError(key)
         self._present.discard(key)
         self._staged.pop(key, None)
+        self._live.pop(key, None)
         self._hostonly.pop(key, None)
         self._removed = True
 
@@ -69,15 +81,22 @@ class PlaneDict(MutableMapping):
             self._removed = True
         self._present.clear()
         self._staged.clear()
+        self._live.clear()
         self._hostonly.clear()
 
     # -- used by the runner --
     def dirty(self):
+        # arrays handed out by __getitem__ and edited in place since become staged writes
+        for key, (arr, orig) in list(self._live.items()):
+            if not np.array_equal(arr, orig):
+                self._staged[key] = arr
+                del self._live[key]
         return bool(self._staged) or self._removed
 
     def device_changed(self, keys_now_present=()):
         """The kernel rewrote (part of) the plane."""
         self._host = None
+        self._live.clear()
         self._present.update(keys_now_present)
 
     def snapshot(self):
@@ -113,6 +132,7 @@ class SquareRunner:
         self.layout, self._order, self._shape = dict(layout), list(order), shape
         for d, vals in zip(self.dicts, saved):
             d._host = None
+            d._live = {}
             d._present = set(vals.keys())
             d._staged = dict(vals)      # re-upload through the flush path
             d._hostonly = {}

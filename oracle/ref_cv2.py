@@ -141,16 +141,21 @@ def cd_update(gray_u8, mean, var, alpha=0.1):
     return nm, nv
 
 
-def full_frame(frame, points, cd_state=None, pd_ref=None, grid=None):
+def full_frame(frame, points, cd_state=None, pd_ref=None, grid=None, keep=None):
     """One frame of the benchmark composition (BASELINE.json configs 1-3): enhance, analysis,
-    warp, 64 squares, PieceDetector statistics, ChangeDetector detect + update."""
+    warp, 64 squares, PieceDetector statistics, ChangeDetector detect + update.
+    `keep` (a dict) receives the enhanced frame, the Otsu mask and the preprocessed squares (parity checks)."""
     enh = process_pipeline(frame)
     _, binary, t = prepare_analysis(enh)
     warped, _, _ = warp_image(enh, points)
     squares = split_board(warped, *(grid or (None, None)))
     res = {}
+    if keep is not None:
+        keep.update(enhanced=enh, binary=binary, gray_squares={})
     for pos, sq in squares.items():
         g = preprocess_square(sq, 5)
+        if keep is not None:
+            keep["gray_squares"][pos] = g
         st = pd_statistics(g, None if pd_ref is None else pd_ref.get(pos))
         if cd_state is not None:
             if pos not in cd_state:

@@ -137,11 +137,11 @@ class FakeEngine:
                     g = O.square_preprocess(sq, p.cd_blur)
                     M = state.planes[_lib.PLANE_CD_MEAN][s, y:y + h, x:x + w]
                     V = state.planes[_lib.PLANE_CD_VAR][s, y:y + h, x:x + w]
-                    has_cd = bool(fl & 2)
+                    has_cd = (fl & 6) == 6
                     if p.ops & SQ_CD_CALIBRATE:
                         m, v = O.cd_calibrate(g, p.initial_variance)
                         M[...] = m; V[...] = v
-                        state.planes[_lib.PLANE_FLAGS][s, y:y + h, x:x + w] |= 2
+                        state.planes[_lib.PLANE_FLAGS][s, y:y + h, x:x + w] |= 6
                         has_cd = True
                     if has_cd:
                         m, v = np.array(M, np.float32), np.array(V, np.float32)
@@ -196,3 +196,18 @@ class FakeEngine:
 
     def hough_state(self, state, rects, params=None, stream0=0, n=1, select=None):
         return self.hough(state.planes[_lib.PLANE_PD_CUR][stream0:stream0 + n], rects, params, select)
+
+    # -- whole path on host frames (cvb_pipeline): enhance -> warp -> squares, composed from the oracle --
+    def pipeline_params(self, enhance=None, squares=None, warp_enhanced=True, board_size=620, rotate_180=False):
+        return dict(enhance=enhance, squares=squares, warp_enhanced=warp_enhanced, board_size=board_size, rotate_180=rotate_180)
+
+    def pipeline(self, frames, M, rects, params, state=None, stream0=0, select=None):
+        frames = np.asarray(frames)
+        n, S = frames.shape[0], params["board_size"]
+        t = np.zeros(n, np.int32)
+        boards = np.zeros((n, S, S, 3), np.uint8)
+        for i in range(n):
+            enh, _, _, t[i] = self.enhance(frames[i])
+            b = O.warp(enh if params["warp_enhanced"] else frames[i], M, S)
+            boards[i] = b[::-1, ::-1] if params["rotate_180"] else b
+        return t, self.squares(boards, rects, params["squares"], state, stream0, select)

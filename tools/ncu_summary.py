@@ -42,9 +42,23 @@ def main():
         for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[c]]) * scale[units[idx[c]]]
         traffic[short] = int(tot / frames)
+    # utilisation of the pipes a kernel can be bound by (percent of peak): bench.py reports the busiest one as `roofline.bound`
+    pipe_cols = {"dram": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                 "lsu": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                 "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                 "fma": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+                 "alu": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+                 "fp64": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"}
+    pipes = {short: {k: round(float(r[idx[c]]), 1) for k, c in pipe_cols.items() if c in idx} for short, r in keep}
+    conflicts = {}
+    for short, r in keep:
+        a, b = "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"
+        if a in idx and b in idx and float(r[idx[a]]) > 0:
+            conflicts[short] = round(float(r[idx[b]]) / float(r[idx[a]]), 3)
     json.dump({"source": "%s: ncu --set full, tools/prof_run.py %d 1 (%d x 1080p board frames per launch), dram__bytes_read.sum + "
                          "dram__bytes_write.sum of the first launch of each kernel / %d" % (out_csv, frames, frames, frames),
-               "dram_bytes_per_frame": traffic}, open(out_json, "w"), indent=1)
+               "dram_bytes_per_frame": traffic, "pipes_pct": pipes, "shared_conflict_share": conflicts},
+              open(out_json, "w"), indent=1)
     for short, r in keep:
         print("%-14s %8.3f ms  issue %5.1f%%  warps %5.1f%%  dram/frame %.2f MB" % (
             short, float(r[idx["gpu__time_duration.sum"]]), float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
