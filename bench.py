@@ -67,14 +67,20 @@ def _cpu_worker(args):
         from oracle import ref_cv2
         cv2.setNumThreads(1)
         cd = {}
+        code = {"yuy2": cv2.COLOR_YUV2BGR_YUY2, "nv12": cv2.COLOR_YUV2BGR_NV12}.get(_INGEST)
         for s in seeds:
-            ref_cv2.full_frame(_FRAMES[s % len(_FRAMES)], pts, cd_state=cd, pd_ref=None)
+            f = _FRAMES[s % len(_FRAMES)]
+            if code is not None:
+                f = cv2.cvtColor(f, code)          # what cv2.VideoCapture does before read() returns (play_lichess.py:45)
+            ref_cv2.full_frame(f, pts, cd_state=cd, pd_ref=None)
             n += 1
     else:
         import oracle as O
         M = O.get_perspective(pts, [[0, 0], [S, 0], [0, S], [S, S]])
         for s in seeds:
             f = _FRAMES[s % len(_FRAMES)]
+            if _INGEST != "bgr":
+                f = O.yuv_to_bgr(f, _INGEST)
             enh = O.process_pipeline(f, True)
             O.prepare_analysis(enh)
             board = O.warp(enh, M, S)
@@ -90,6 +96,7 @@ def _cpu_worker(args):
 
 
 _FRAMES = None
+_INGEST = "bgr"
 
 
 def cpu_reference(frames, n_frames, pool, kind):
@@ -104,11 +111,11 @@ def cpu_reference(frames, n_frames, pool, kind):
     return done / dt, dt
 
 
-def make_pool(frames):
+def make_pool(frames, ingest="bgr"):
     """Fork-based pool created BEFORE any CUDA context exists in this process."""
     import multiprocessing as mp
-    global _FRAMES
-    _FRAMES = frames
+    global _FRAMES, _INGEST
+    _FRAMES, _INGEST = frames, ingest
     try:
         import cv2  # noqa: F401
         kind = "cv2"
@@ -198,6 +205,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--kind", default="board", choices=["board", "noise"])
+    ap.add_argument("--config", default="throughput", choices=["throughput", "latency", "change64", "streams4k"],
+                    help="throughput = BASELINE.json configs[3] (the metric; default); latency = configs[1]; change64 = configs[2]; "
+                         "streams4k = configs[4] (tools/bench_modes.py)")
+    ap.add_argument("--ingest", default="bgr", choices=["bgr", "yuy2", "nv12"],
+                    help="format the frames arrive in: BGR as cv2.VideoCapture.read() returns them (BASELINE configs), or the "
+                         "camera's native YUY2 / NV12, converted to BGR on the device (this arm) or by cv2.cvtColor (reference arm)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0: 4 per host core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the single-frame latency / config-3 side measurements")
@@ -225,6 +238,9 @@ def main():
                           "(LAB+CLAHE+bilateral d=9+sharpen+normalize, gray+blur+Otsu mask, warp to 620x620, 64 squares, "
                           "piece_detector statistics + change_detector detect/update)" % args.frames,
               "frames_per_gpu": args.frames, "height": H, "width": W, "frame_kind": args.kind,
+              "ingest": args.ingest + {"bgr": " (3 bytes / pixel, as cv2.VideoCapture.read() returns frames)",
+                                       "yuy2": " (camera-native, 2 bytes / pixel, converted on the device like cv2.cvtColor)",
+                                       "nv12": " (decoder-native, 1.5 bytes / pixel, converted on the device like cv2.cvtColor)"}[args.ingest],
               "unique_frames": UNIQUE, "parallelism": "frames sharded over %d GPU(s), no collective" % world,
               "numa": "each rank pinned to its GPU's CPUs (NVML affinity) before allocating page-locked buffers",
               "l2_policy": "inputs larger than L2 (%.0f MB per step per GPU vs 126 MB)" % (args.frames * H * W * 3 / 1e6)}
@@ -234,7 +250,9 @@ def main():
         if rank != 0:
             return
         frames = synth.frame_batch(UNIQUE, H, W, args.kind, 0)
-        pool, kind, cores = make_pool(frames)
+        if args.ingest != "bgr":
+            frames = np.stack([synth.bgr_to_yuv(f, args.ingest) for f in frames])
+        pool, kind, cores = make_pool(frames, args.ingest)
         per_step = args.cpu_frames or 2 * cores
         for _ in range(args.warmup):
             cpu_reference(frames, per_step, pool, kind)
@@ -261,11 +279,12 @@ def main():
 
     # ------------------------------------------------------------------ this repo's arm
     frames_u = synth.frame_batch(UNIQUE, H, W, args.kind, 0)
+    native_u = frames_u if args.ingest == "bgr" else np.stack([synth.bgr_to_yuv(f, args.ingest) for f in frames_u])
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        pool, kind, cores = make_pool(frames_u)          # fork before CUDA
+        pool, kind, cores = make_pool(native_u, args.ingest)          # fork before CUDA
         n_cpu = args.cpu_frames or 4 * cores
-        fps_cpu, dt_cpu = cpu_reference(frames_u, n_cpu, pool, kind)
+        fps_cpu, dt_cpu = cpu_reference(native_u, n_cpu, pool, kind)
         pool.close()
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d of the %d frames of one step, %.1f s wall, %d processes x 1 OpenCV thread" %
@@ -286,27 +305,6 @@ def main():
                                                SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
     eng = Engine(local_rank)
     n = args.frames
-    rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
-    M = eng.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
-    state = eng.new_state(n, S, S)
-
-    # host batch in pinned memory (e2e source) and a resident device copy (kernel-only source)
-    host = eng.pinned((n, H, W, 3))
-    for i in range(n):
-        host[i] = frames_u[(i + rank) % UNIQUE]
-    d_in = eng.empty((n, H, W, 3))
-    eng.lib.cvb_memcpy_h2d(eng.h, d_in.ptr, host.ctypes.data, host.nbytes)
-    d_stats = eng.empty((n, len(rects)), STATS_DTYPE)
-    d_otsu = eng.empty((n,), np.int32)
-    eng.synchronize()
-
-    sq_cal = eng.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE)
-    sq_run = eng.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE)
-    pp_cal = eng.pipeline_params(squares=sq_cal, board_size=S)
-    pp = eng.pipeline_params(squares=sq_run, board_size=S)
-    # calibration frame: references + background model for every stream slot (untimed)
-    eng.pipeline_dev(d_in, M, rects, pp_cal, state, stats=d_stats, otsu_t=d_otsu)
-    eng.synchronize()
 
     def barrier():
         eng.synchronize()
@@ -314,15 +312,6 @@ def main():
             import torch
             dist.barrier()
             torch.cuda.synchronize()
-
-    def run_dev(k):
-        for _ in range(k):
-            eng.pipeline_dev(d_in, M, rects, pp, state, stats=d_stats, otsu_t=d_otsu)
-
-    def run_e2e(k):
-        for _ in range(k):
-            eng.lib  # the public host-buffer call: H2D + kernels + D2H of per-square results
-            eng.pipeline(host, M, rects, pp, state)
 
     def timed(fn, k):
         barrier()
@@ -340,6 +329,62 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, launches
+
+    if args.config != "throughput":
+        # the other BASELINE configurations (tools/bench_modes.py): same JSON contract, their own metric
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_modes
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.wait_ready()
+        wall0 = time.time()
+        out = bench_modes.MODES[args.config]({"eng": eng, "synth": synth, "args": args, "rank": rank, "world": world,
+                                              "timed": timed})
+        clocks = sampler.stop(wall0, time.time()) if sampler else None
+        if rank == 0:
+            out.update({"n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "scaling": "weak", "vs_baseline": None,
+                        "dtype": "u8 (f32 bilateral / CLAHE blend, f64 Otsu and warp coordinates)", "data": "synthetic",
+                        "clocks": clocks})
+            emit(out)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    M = eng.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
+    state = eng.new_state(n, S, S)
+
+    # host batch in pinned memory (e2e source) and a resident device copy (kernel-only source), both in the ingest format
+    host = eng.pinned((n,) + native_u.shape[1:])
+    for i in range(n):
+        host[i] = native_u[(i + rank) % UNIQUE]
+    d_native = eng.empty(host.shape)
+    eng.lib.cvb_memcpy_h2d(eng.h, d_native.ptr, host.ctypes.data, host.nbytes)
+    d_in = d_native if args.ingest == "bgr" else eng.empty((n, H, W, 3))
+    d_stats = eng.empty((n, len(rects)), STATS_DTYPE)
+    d_otsu = eng.empty((n,), np.int32)
+    eng.synchronize()
+
+    sq_cal = eng.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE)
+    sq_run = eng.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE)
+    pp_cal = eng.pipeline_params(squares=sq_cal, board_size=S)
+    pp = eng.pipeline_params(squares=sq_run, board_size=S)
+    # calibration frame: references + background model for every stream slot (untimed)
+    if args.ingest != "bgr":
+        eng.cvt_to_bgr_dev(d_native, args.ingest, n, H, W, d_in)
+    eng.pipeline_dev(d_in, M, rects, pp_cal, state, stats=d_stats, otsu_t=d_otsu)
+    eng.synchronize()
+
+    def run_dev(k):
+        for _ in range(k):
+            if args.ingest != "bgr":
+                eng.cvt_to_bgr_dev(d_native, args.ingest, n, H, W, d_in)
+            eng.pipeline_dev(d_in, M, rects, pp, state, stats=d_stats, otsu_t=d_otsu)
+
+    def run_e2e(k):
+        for _ in range(k):
+            eng.lib  # the public host-buffer call: H2D + kernels + D2H of per-square results
+            eng.pipeline(host, M, rects, pp, state, fmt=args.ingest)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -359,65 +404,46 @@ def main():
     run_e2e(args.warmup)
     ms_e2e, _ = timed(run_e2e, args.steps)
 
-    # ---- side measurements for the other BASELINE.json configs (rank 0, not part of value/e2e) ----
+    # ---- side measurements (rank 0, not part of value/e2e): the other BASELINE.json configurations through the very
+    # functions of `--config latency|change64|streams4k` (short runs), the worst-case input kind, and the end-to-end
+    # rate when the frames arrive in the camera's native format instead of BGR ----
     extras = {}
-    if rank == 0 and not args.no_extras:
-        one = eng.empty((1, H, W, 3))
-        eng.lib.cvb_memcpy_h2d(eng.h, one.ptr, host.ctypes.data, H * W * 3)
-        st1 = eng.new_state(1, S, S)
-        s1 = eng.empty((1, len(rects)), STATS_DTYPE); o1 = eng.empty((1,), np.int32)
-        eng.pipeline_dev(one, M, rects, pp_cal, st1, stats=s1, otsu_t=o1)
-        lat = []
-        for _ in range(25):
-            e0, e1 = eng.event(), eng.event()
-            eng.record(e0); eng.pipeline_dev(one, M, rects, pp, st1, stats=s1, otsu_t=o1); eng.record(e1)
-            lat.append(eng.elapsed_ms(e0, e1))
-        lat_host = []
-        for _ in range(25):
-            t0 = time.perf_counter(); eng.pipeline(host[:1], M, rects, pp, st1); lat_host.append((time.perf_counter() - t0) * 1e3)
-        extras["config2_single_1080p_frame"] = {"device_ms_median": float(np.median(lat[5:])),
-                                                "host_call_ms_median": float(np.median(lat_host[5:])),
-                                                "what": "enhance + analysis + warp + 64 squares + statistics, one frame"}
-        # config 3: per-square change statistics on 64 consecutive-frame pairs (warp + square kernel only)
-        nb = 64
-        boards_in = eng.empty((nb, H, W, 3))
-        eng.lib.cvb_memcpy_h2d(eng.h, boards_in.ptr, host.ctypes.data, nb * H * W * 3)
-        warped = eng.empty((nb, S, S, 3)); st3 = eng.new_state(nb, S, S); s3 = eng.empty((nb, len(rects)), STATS_DTYPE)
-        eng.lib.cvb_warp_dev(eng.h, boards_in.ptr, nb, H, W, M.ctypes.data, 1, S, S, warped.ptr)
-        eng.squares(warped, rects, sq_cal, st3, want_stats=False)
-        rect_arr = _rect_array(rects)
-        e0, e1 = eng.event(), eng.event()
-        eng.record(e0)
-        for _ in range(10):
-            eng.lib.cvb_warp_dev(eng.h, boards_in.ptr, nb, H, W, M.ctypes.data, 1, S, S, warped.ptr)
-            eng.lib.cvb_squares_dev(eng.h, warped.ptr, nb, S, S, 3, ctypes.cast(rect_arr, ctypes.c_void_p),
-                                    len(rects), None, st3.ptr, 0, ctypes.byref(sq_run), s3.ptr)
-        eng.record(e1)
-        ms3 = eng.elapsed_ms(e0, e1) / 10
-        extras["config3_change_stats_64_pairs"] = {"ms_per_batch": ms3, "frames_per_s": nb / ms3 * 1e3,
-                                                   "what": "warp + 64 squares: absdiff delta, moments, centre/border, rings, "
-                                                           "z-score detect + EMA update (resident inputs)"}
-        # config 4 shape: 8 concurrent 3840x2160 camera streams on this GPU (64 streams over 8 GPUs), one frame each per step
-        n4, H4, W4 = 8, 2160, 3840
-        f4 = np.stack([synth.board_frame(H4, W4, 40 + i) for i in range(2)])
-        d4 = eng.upload(np.stack([f4[i % 2] for i in range(n4)]))
-        M4 = eng.get_perspective_transform(synth.calib_points(H4, W4), [[0, 0], [S, 0], [0, S], [S, S]])
-        st4 = eng.new_state(n4, S, S); s4 = eng.empty((n4, len(rects)), STATS_DTYPE); o4 = eng.empty((n4,), np.int32)
-        eng.pipeline_dev(d4, M4, rects, pp_cal, st4, stats=s4, otsu_t=o4)
-        for _ in range(2):
-            eng.pipeline_dev(d4, M4, rects, pp, st4, stats=s4, otsu_t=o4)
-        e0, e1 = eng.event(), eng.event()
-        eng.record(e0)
-        for _ in range(5):
-            eng.pipeline_dev(d4, M4, rects, pp, st4, stats=s4, otsu_t=o4)
-        eng.record(e1)
-        ms4 = eng.elapsed_ms(e0, e1) / 5
-        extras["config4_8_streams_4k"] = {"ms_per_step": ms4, "frames_per_s": n4 / ms4 * 1e3,
-                                          "mpixels_per_s": n4 * H4 * W4 / ms4 / 1e3,
-                                          "what": "8 resident 3840x2160 streams per GPU, full path with per-stream state"}
-        for x in (d4, s4, o4):
-            x.free()
-        st4.free()
+    if rank == 0 and not args.no_extras and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_modes
+        side = argparse.Namespace(**vars(args)); side.steps, side.warmup, side.kind = 10, 3, "board"
+        for name in ("latency", "change64", "streams4k"):
+            r = bench_modes.MODES[name]({"eng": eng, "synth": synth, "args": side, "rank": 0, "world": 1, "timed": timed})
+            extras["config_" + name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "cpu_baseline",
+                                                          "stages_us") if k in r}
+            extras["config_" + name]["workload"] = r["config"]["workload"]
+        if args.ingest == "bgr":
+            other = "noise" if args.kind == "board" else "board"
+            fo = synth.frame_batch(UNIQUE, H, W, other, 0)
+            for i in range(n):
+                host[i] = fo[i % UNIQUE]
+            eng.lib.cvb_memcpy_h2d(eng.h, d_in.ptr, host.ctypes.data, host.nbytes)
+            run_dev(3)
+            ms_o, _ = timed(run_dev, 5)
+            extras["frame_kind_" + other] = {"value": n * 5 / (ms_o / 1e3), "unit": "frames/s", "ms_per_step": ms_o / 5,
+                                             "what": "the resident-input number of this line on '%s' frames (SURVEY.md 8d: uniform "
+                                                     "noise is the worst case for the histogram atomics and the range-weight "
+                                                     "lookups)" % other}
+            for fmt in ("yuy2", "nv12"):
+                nat = np.stack([synth.bgr_to_yuv(f, fmt) for f in frames_u])
+                hn = eng.pinned((n,) + nat.shape[1:])
+                for i in range(n):
+                    hn[i] = nat[i % UNIQUE]
+                run_n = lambda k: [eng.pipeline(hn, M, rects, pp, state, fmt=fmt) for _ in range(k)]
+                run_n(3)
+                ms_n, _ = timed(run_n, 8)
+                extras["e2e_ingest_" + fmt] = {"value": n * 8 / (ms_n / 1e3), "unit": "frames/s", "ms_per_step": ms_n / 8,
+                                               "h2d_bytes_per_step": int(hn.nbytes),
+                                               "what": "the e2e number of this line with frames arriving as %s (%.1f bytes per "
+                                                       "pixel over PCIe), converted on the device bit-exactly as cv2.cvtColor "
+                                                       "does (`--ingest %s` makes it the headline of both arms)" %
+                                                       (fmt.upper(), hn.nbytes / (n * H * W), fmt)}
+                eng.lib.cvb_host_free(hn.ctypes.data)
         # "next" row: Hough circles on the 64 gray+blur squares of warped boards with pieces (k_hough),
         # beside the reference's cv2.HoughCircles loop on this box's host cores
         nh = 64
@@ -452,9 +478,6 @@ def main():
             "what": "cv2.HoughCircles(dp 1.2, 100/25, radii 20-55 %) on 64 squares per frame, one CTA per square; "
                     "CPU: the reference's loop over 64 squares with cv2 (its default threads), 2 frames"}
         sth.free()
-        for x in (one, s1, o1, boards_in, warped, s3):
-            x.free()
-        st1.free(); st3.free()
 
     # ---- parity beside the throughput number: the reference's cv2 / numpy call sequence against the
     # CUDA path on (previous, current) pairs of the very frame kinds that are timed: Otsu T, mask per pixel, change flags

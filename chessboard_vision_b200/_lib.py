@@ -81,6 +81,8 @@ assert C.sizeof(HoughParams) == 56 and C.sizeof(HoughSquare) == 40 and C.sizeof(
 
 SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE = 1, 2, 4, 8, 16
 PLANE_PD_REF, PLANE_CD_MEAN, PLANE_CD_VAR, PLANE_PD_CUR, PLANE_FLAGS = 0, 1, 2, 3, 4
+FMT_BGR, FMT_YUY2, FMT_NV12 = 0, 1, 2
+FORMATS = {"bgr": FMT_BGR, "yuy2": FMT_YUY2, "nv12": FMT_NV12}
 
 # every symbol include/cvb200.h declares: (name, restype, argtypes)
 _P, _I, _D, _SZ = C.c_void_p, C.c_int, C.c_double, C.c_size_t
@@ -150,6 +152,9 @@ SYMBOLS = [
                               _P, _P, _P, _P, _P, _P]),
     ("cvb_set_chunk_frames", _I, [_P, _I]),
     ("cvb_pipeline", _I, [_P, _P, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    ("cvb_frame_bytes", _SZ, [_I, _I, _I]),
+    ("cvb_cvt_to_bgr_dev", _I, [_P, _P, _I, _I, _I, _I, _P]),
+    ("cvb_pipeline_fmt", _I, [_P, _P, _I, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
 ]
 
 _lib = None

@@ -115,7 +115,7 @@ void cvb_destroy(cvb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
+    DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_raw, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
                       &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks,
                       &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res};
@@ -892,18 +892,52 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, con
                            otsu_t, warped, stats);
 }
 
+size_t cvb_frame_bytes(int format, int H, int W) { return cvb_host_frame_bytes(format, H, W); }
+
+int cvb_cvt_to_bgr_dev(cvb_handle *h, const uint8_t *src, int format, int n, int H, int W, uint8_t *bgr)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(src && bgr && src != bgr, "null or aliased image pointer");
+    if (format == CVB_FMT_BGR) {
+        CVB_CHECK_CUDA(cudaMemcpyAsync(bgr, src, (size_t)n * H * W * 3, cudaMemcpyDeviceToDevice, h->stream));
+        return CVB_OK;
+    }
+    return launch_yuv_to_bgr(h, src, format, n, H, W, bgr);
+}
+
 // Host-buffer variant.  The batch is cut into chunks; chunk k+1 is copied host->device on a second
 // stream while chunk k is being processed (two input buffers), so the PCIe copy and the kernels
-// overlap when the host memory is page-locked.
-int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p, const double *M9,
-                 int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state, int stream0,
-                 int32_t *otsu_t, cvb_square_stats *stats)
+// overlap when the host memory is page-locked.  Frames arrive in `format`; YUV frames are converted
+// to BGR on the device (cvb_ingest.cu), so only their 2 or 1.5 bytes per pixel cross PCIe.
+int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W, const cvb_pipeline_params *p,
+                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state,
+                     int stream0, int32_t *otsu_t, cvb_square_stats *stats)
 {
-    CVB_TRY(pipeline_check(h, bgr, n, H, W, p, M9, n_mats, rects));
+    CVB_TRY(pipeline_check(h, frames, n, H, W, p, M9, n_mats, rects));
     CVB_REQUIRE(n_sq >= 1, "no squares");
+    CVB_REQUIRE(format == CVB_FMT_BGR || format == CVB_FMT_YUY2 || format == CVB_FMT_NV12, "unknown frame format %d", format);
+    CVB_REQUIRE(format == CVB_FMT_BGR || (W % 2 == 0 && (format != CVB_FMT_NV12 || H % 2 == 0)),
+                "YUV frames need an even width (NV12: and height), got %dx%d", W, H);
     const int S = p->board_size;
-    const size_t fb = (size_t)H * W * 3;
-    const int chunk = std::max(1, std::min(n, h->chunk_frames));
+    const size_t fb = (size_t)H * W * 3, fin = cvb_host_frame_bytes(format, H, W);
+    // Frames per chunk.  Measured on B200 at 1080p (tools/chunk_sweep.py, profiles/r02_notes.md): BGR input is bound by
+    // the PCIe copy and wants small chunks (the first chunk's copy is the only one not overlapped: 4..13 frames equal);
+    // YUV input is bound by the kernels, which want chunks whose fused-kernel grid fills whole waves of 2 CTAs per SM
+    // (25 frames at 1080p: 6800 CTAs = 22.97 waves; 8 frames = 7.35 waves lose 8 %).
+    int chunk = h->chunk_frames;
+    if (chunk <= 0) {
+        chunk = 8;
+        if (format != CVB_FMT_BGR) {
+            const long tiles = (long)((W + 119) / 120) * ((H + 63) / 64), slots = 2L * h->sm_count;
+            double best = 0;
+            for (int c = 12; c <= 32; ++c) {
+                const long ctas = tiles * c, waves = (ctas + slots - 1) / slots;
+                const double eff = (double)ctas / (double)(waves * slots);
+                if (eff >= best) { best = eff; chunk = c; }
+            }
+        }
+    }
+    chunk = std::max(1, std::min(n, chunk));
     if (!h->copy_stream) {
         CVB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
@@ -911,7 +945,11 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const c
             CVB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
         }
     }
-    WS(ws_in, uint8_t, fb * chunk * 2, d_in);
+    // two staging buffers of one chunk in the arrival format; YUV chunks are converted into one BGR buffer
+    DevBuf &stage = format == CVB_FMT_BGR ? h->ws_in : h->ws_raw;
+    uint8_t *d_in = nullptr, *d_bgr = nullptr;
+    CVB_TRY(cvb_ws(h, stage, fin * chunk * 2, (void **)&d_in));
+    if (format != CVB_FMT_BGR) CVB_TRY(cvb_ws(h, h->ws_in, fb * chunk, (void **)&d_bgr));
     WS(ws_stats, cvb_square_stats, (size_t)n * n_sq, d_stats);
     WS(ws_otsu_all, int32_t, n, d_otsu);
     double *d_m = nullptr;
@@ -929,21 +967,28 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const c
         CVB_TRY(cvb_ws(h, h->ws_sharp, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_blur, npx * chunk, &t));
         CVB_TRY(cvb_ws(h, h->ws_lab, fb * chunk, &t));
     }
-    // the copy stream must not start before earlier work on the compute stream that reads ws_in is done
+    // the copy stream must not start before earlier work on the compute stream that reads the staging buffers is done
     CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[0], h->stream));
     CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
     int k = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ++k) {
         const int cnt = std::min(chunk, n - f0), b = k & 1;
-        uint8_t *buf = d_in + (size_t)b * chunk * fb;
+        uint8_t *buf = d_in + (size_t)b * chunk * fin;
         if (k >= 2) CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
-        CVB_CHECK_CUDA(cudaMemcpyAsync(buf, bgr + (size_t)f0 * fb, fb * cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CVB_CHECK_CUDA(cudaMemcpyAsync(buf, frames + (size_t)f0 * fin, fin * cnt, cudaMemcpyHostToDevice, h->copy_stream));
         CVB_CHECK_CUDA(cudaEventRecord(h->ev_copy[b], h->copy_stream));
         CVB_CHECK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
-        CVB_TRY(pipeline_launch(h, buf, cnt, H, W, p, n_mats == 1 ? d_m : d_m + (size_t)9 * f0, n_mats == 1 ? 1 : cnt, rects,
+        const uint8_t *bgr = buf;
+        if (format != CVB_FMT_BGR) {
+            CVB_TRY(launch_yuv_to_bgr(h, buf, format, cnt, H, W, d_bgr));
+            // the staging buffer is free again as soon as the conversion has read it
+            CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+            bgr = d_bgr;
+        }
+        CVB_TRY(pipeline_launch(h, bgr, cnt, H, W, p, n_mats == 1 ? d_m : d_m + (size_t)9 * f0, n_mats == 1 ? 1 : cnt, rects,
                                 n_sq, select, state, stream0 + f0, nullptr, nullptr, nullptr, d_otsu + f0, nullptr,
                                 d_stats + (size_t)f0 * n_sq));
-        CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+        if (format == CVB_FMT_BGR) CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
     }
     if (stats)
         CVB_CHECK_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(cvb_square_stats) * (size_t)n * n_sq,
@@ -953,10 +998,17 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const c
     return CVB_OK;
 }
 
+int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p, const double *M9,
+                 int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state, int stream0,
+                 int32_t *otsu_t, cvb_square_stats *stats)
+{
+    return cvb_pipeline_fmt(h, bgr, CVB_FMT_BGR, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, otsu_t, stats);
+}
+
 int cvb_set_chunk_frames(cvb_handle *h, int frames)
 {
     REQ_H(h);
-    CVB_REQUIRE(frames >= 1, "chunk must be >= 1 frame");
+    CVB_REQUIRE(frames >= 0, "chunk must be >= 1 frame, or 0 for the library's choice");
     h->chunk_frames = frames;
     return CVB_OK;
 }

@@ -79,12 +79,12 @@ struct cvb_handle {
     float *d_color = nullptr;
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
-    DevBuf ws_lab, ws_prof, ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
+    DevBuf ws_lab, ws_prof, ws_in, ws_raw, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
     DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    int chunk_frames = 8;
+    int chunk_frames = 0;       // frames per chunk of the host-buffer pipeline; 0 = chosen per call (cvb_pipeline_fmt)
     // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
     DevBuf ws_masks;
     // Hough: staged per-square geometry (content-compared), select bytes, results
@@ -153,6 +153,10 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
                   uint8_t *enhanced, uint8_t *gray, uint8_t *blurred, int32_t *hist);
 int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t);
 int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const int32_t *otsu_t, uint8_t *dst);
+
+// ---- cvb_ingest.cu ------------------------------------------------------------------------
+size_t cvb_host_frame_bytes(int format, int H, int W);
+int launch_yuv_to_bgr(cvb_handle *h, const uint8_t *src, int format, int n, int H, int W, uint8_t *bgr);
 
 // ---- cvb_canny.cu -------------------------------------------------------------------------
 int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh, uint8_t *edges);

@@ -459,6 +459,21 @@ class Engine:
         check(fn(self.h, src.ptr, n, H, W, M.ctypes.data, n_mats, int(oh), int(ow), dst.ptr))
         return self._out(dst, tmp, [src] if tmp else [])
 
+    def warp_dev(self, src, M, size, dst, rotate_180=False):
+        """Device buffers: (n,H,W,3) -> (n,size,size,3); nothing is copied or synchronised."""
+        M = np.ascontiguousarray(M, np.float64)
+        n, H, W = src.shape[0], src.shape[1], src.shape[2]
+        fn = self.lib.cvb_warp_rot180_dev if rotate_180 else self.lib.cvb_warp_dev
+        check(fn(self.h, src.ptr, n, H, W, M.ctypes.data, 1 if M.ndim == 2 else M.shape[0], int(size), int(size), dst.ptr))
+
+    def squares_dev(self, boards, rects, params, state, stream0, stats):
+        """Device buffers: boards (n,BH,BW,3) -> stats (n, n_sq) on the device (may be None)."""
+        n, BH, BW = boards.shape[0], boards.shape[1], boards.shape[2]
+        ra = rects if not isinstance(rects, (list, tuple)) else _rect_array(rects)
+        check(self.lib.cvb_squares_dev(self.h, boards.ptr, n, BH, BW, boards.shape[3] if len(boards.shape) == 4 else 1,
+                                       C.cast(ra, C.c_void_p), len(ra), None, state.ptr if state is not None else None,
+                                       int(stream0), C.byref(params), stats.ptr if stats is not None else None))
+
     def rotate(self, img, code):
         """cv2.rotate(img, code) for (H,W) / (H,W,3) / (n,H,W,3) u8; code 0: 90 cw, 1: 180, 2: 90 ccw."""
         shape = tuple(img.shape)
@@ -649,19 +664,57 @@ class Engine:
         p.rotate_180 = int(bool(rotate_180))
         return p
 
-    def pipeline(self, frames, M, rects, params, state=None, stream0=0, select=None):
-        """HOST frames (n,H,W,3) -> (otsu_t[n], stats[n, n_sq]); H2D and D2H happen inside the call."""
+    # -- camera ingest (play_lichess.py:16-18,45) -------------------------------
+    @staticmethod
+    def _frame_geometry(frames, fmt):
+        """-> (n, H, W) of host / device frames in `fmt`: 'bgr' (n,H,W,3), 'yuy2' (n,H,W,2), 'nv12' (n,H*3/2,W);
+        a single frame may omit the leading axis."""
+        shp = tuple(frames.shape)
+        if fmt == "nv12":
+            if len(shp) == 2:
+                shp = (1,) + shp
+            if len(shp) != 3 or shp[1] % 3 or (shp[1] * 2 // 3) % 2 or shp[2] % 2:
+                raise ValueError("NV12 frames are (H * 3 / 2, W) with even H and W, got %r" % (frames.shape,))
+            return shp[0], shp[1] * 2 // 3, shp[2]
+        ch = {"bgr": 3, "yuy2": 2}[fmt]
+        if len(shp) == 3:
+            shp = (1,) + shp
+        if len(shp) != 4 or shp[3] != ch or (fmt == "yuy2" and shp[2] % 2):
+            raise ValueError("%s frames are (H, W, %d)%s, got %r" % (fmt, ch, " with even W" if fmt == "yuy2" else "", frames.shape))
+        return shp[0], shp[1], shp[2]
+
+    def cvt_to_bgr(self, frames, fmt):
+        """cv2.cvtColor(frame, COLOR_YUV2BGR_YUY2 / COLOR_YUV2BGR_NV12) on the device -> BGR (n,H,W,3) or (H,W,3)."""
         frames = np.ascontiguousarray(frames, np.uint8)
-        single, n, H, W = _as_batch(frames, 3)
+        n, H, W = self._frame_geometry(frames, fmt)
+        single = frames.ndim == (2 if fmt == "nv12" else 3)
+        src = self.upload(frames)
+        dst = self.empty((H, W, 3) if single else (n, H, W, 3))
+        check(self.lib.cvb_cvt_to_bgr_dev(self.h, src.ptr, _lib.FORMATS[fmt], n, H, W, dst.ptr))
+        out = dst.get()
+        src.free(); dst.free()
+        return out
+
+    def cvt_to_bgr_dev(self, src, fmt, n, H, W, dst):
+        """Device buffers: n native frames -> n BGR frames."""
+        check(self.lib.cvb_cvt_to_bgr_dev(self.h, src.ptr, _lib.FORMATS[fmt], int(n), int(H), int(W), dst.ptr))
+
+    def pipeline(self, frames, M, rects, params, state=None, stream0=0, select=None, fmt="bgr"):
+        """HOST frames -> (otsu_t[n], stats[n, n_sq]); H2D and D2H happen inside the call.  `fmt`: 'bgr' (n,H,W,3),
+        or the camera's native 'yuy2' (n,H,W,2) / 'nv12' (n,H*3/2,W), converted to BGR on the device exactly as
+        cv2.cvtColor does, so that 2 / 1.5 instead of 3 bytes per pixel cross PCIe."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, H, W = self._frame_geometry(frames, fmt)
         M = np.ascontiguousarray(M, np.float64)
         n_mats = 1 if M.ndim == 2 else M.shape[0]
         ra = _rect_array(rects)
         stats = np.empty((n, len(rects)), STATS_DTYPE); t = np.empty(n, np.int32)
         sel = np.ascontiguousarray(select, np.uint8) if select is not None else None
-        check(self.lib.cvb_pipeline(self.h, frames.ctypes.data, n, H, W, C.byref(params), M.ctypes.data, n_mats,
-                                    C.cast(ra, C.c_void_p), len(rects), sel.ctypes.data if sel is not None else None,
-                                    state.ptr if state is not None else None, int(stream0), t.ctypes.data,
-                                    stats.ctypes.data))
+        check(self.lib.cvb_pipeline_fmt(self.h, frames.ctypes.data, _lib.FORMATS[fmt], n, H, W, C.byref(params),
+                                        M.ctypes.data, n_mats, C.cast(ra, C.c_void_p), len(rects),
+                                        sel.ctypes.data if sel is not None else None,
+                                        state.ptr if state is not None else None, int(stream0), t.ctypes.data,
+                                        stats.ctypes.data))
         return t, stats
 
     def pipeline_dev(self, src, M, rects, params, state=None, stream0=0, select=None, enhanced=None, gray=None,

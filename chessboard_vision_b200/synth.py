@@ -114,3 +114,30 @@ def table_scene(H, W, seed=1):
     img[inside] = (190, 200, 210)
     img += rng.normal(0, 3, img.shape).astype(np.float32)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def bgr_to_yuv(frame, fmt):
+    """A camera-native frame ('yuy2': (H,W,2), 'nv12': (H*3/2,W)) showing roughly `frame` (BT.601 studio range, chroma
+    of each pixel pair / 2x2 block averaged).  Only used to synthesise ingest inputs: what matters downstream is the
+    exact YUV -> BGR step, not this one."""
+    f = frame.astype(np.float32)
+    b, g, r = f[..., 0], f[..., 1], f[..., 2]
+    y = 16 + 0.257 * r + 0.504 * g + 0.098 * b
+    u = 128 - 0.148 * r - 0.291 * g + 0.439 * b
+    v = 128 + 0.439 * r - 0.368 * g - 0.071 * b
+    q = lambda a: np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    H, W = y.shape
+    if fmt == "yuy2":
+        out = np.empty((H, W, 2), np.uint8)
+        out[..., 0] = q(y)
+        out[:, 0::2, 1] = q((u[:, 0::2] + u[:, 1::2]) / 2)
+        out[:, 1::2, 1] = q((v[:, 0::2] + v[:, 1::2]) / 2)
+        return out
+    if fmt == "nv12":
+        out = np.empty((H * 3 // 2, W), np.uint8)
+        out[:H] = q(y)
+        uv = out[H:].reshape(H // 2, W // 2, 2)
+        uv[..., 0] = q((u[0::2, 0::2] + u[0::2, 1::2] + u[1::2, 0::2] + u[1::2, 1::2]) / 4)
+        uv[..., 1] = q((v[0::2, 0::2] + v[0::2, 1::2] + v[1::2, 0::2] + v[1::2, 1::2]) / 4)
+        return out
+    raise ValueError(fmt)

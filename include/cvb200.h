@@ -342,7 +342,8 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                      uint8_t *warped, cvb_square_stats *stats);
 /* host-buffer variant (the call the Python shim times as "e2e"): bgr HOST
  * (pinned or pageable) in; stats / otsu_t HOST out.  The batch is processed
- * in chunks of cvb_set_chunk_frames() frames (default 8): the host->device
+ * in chunks of cvb_set_chunk_frames() frames (default 0 = the library's choice:
+ * 8 for BGR input, wave-sized chunks of 12..32 for YUV input): the host->device
  * copy of chunk k+1 overlaps the kernels of chunk k when bgr is page-locked. */
 int cvb_set_chunk_frames(cvb_handle *h, int frames);
 int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
@@ -351,6 +352,29 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                  const cvb_rect *rects, int n_sq, const uint8_t *select,
                  cvb_state *state, int stream0,
                  int32_t *otsu_t, cvb_square_stats *stats);
+
+/* ---- camera ingest ---------------------------------------------- */
+/* play_lichess.py:16-18,45 / game_session.py:99,113 receive BGR frames from
+ * cv2.VideoCapture.read(), i.e. after OpenCV has converted the camera's native YUV on the
+ * host.  These entry points take the native frame instead and convert on the device,
+ * bit-exactly as cv2.cvtColor(COLOR_YUV2BGR_YUY2 / COLOR_YUV2BGR_NV12) does:
+ *   CVB_FMT_BGR   (H, W, 3)        3   bytes / pixel  (no conversion)
+ *   CVB_FMT_YUY2  (H, W, 2)        2   bytes / pixel  Y0 U Y1 V, W even
+ *   CVB_FMT_NV12  (H * 3 / 2, W)   1.5 bytes / pixel  Y plane, then interleaved U V rows; W, H even */
+#define CVB_FMT_BGR  0
+#define CVB_FMT_YUY2 1
+#define CVB_FMT_NV12 2
+size_t cvb_frame_bytes(int format, int H, int W);
+/* src, bgr: DEVICE.  n frames of cvb_frame_bytes() each -> n BGR frames. */
+int cvb_cvt_to_bgr_dev(cvb_handle *h, const uint8_t *src, int format, int n, int H, int W, uint8_t *bgr);
+/* cvb_pipeline on frames in their native format (HOST, pinned or pageable): only
+ * cvb_frame_bytes() per frame cross PCIe; cvb_pipeline(...) == cvb_pipeline_fmt(..., CVB_FMT_BGR, ...). */
+int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W,
+                     const cvb_pipeline_params *p,
+                     const double *M9, int n_mats,
+                     const cvb_rect *rects, int n_sq, const uint8_t *select,
+                     cvb_state *state, int stream0,
+                     int32_t *otsu_t, cvb_square_stats *stats);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

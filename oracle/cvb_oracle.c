@@ -1143,3 +1143,37 @@ ORC_API void orc_refine_grid(const u8 *bgr, int H, int W, int32_t *grid_x9, int3
     internal_lines(rows, H, grid_y9);
     free(g); if (!edges_out) free(e); free(rows); free(cols);
 }
+
+/* Camera ingest (play_lichess.py:16-18,45 -- cv2.VideoCapture delivers BGR by running these   */
+/* conversions on the camera's native packed / semi-planar YUV).  cv2.cvtColor(COLOR_YUV2BGR_YUY2 / _NV12),          */
+/* imgproc/src/color_yuv.simd.hpp (ITU-R BT.601, 20 fractional bits):                                                */
+/*   yy = max(0, y - 16) * 1220542;  r = (yy + 2^19 + 1673527 (v-128)) >> 20;                                        */
+/*   g = (yy + 2^19 - 852492 (v-128) - 409993 (u-128)) >> 20;  b = (yy + 2^19 + 2116026 (u-128)) >> 20;  saturate.   */
+/* fmt 1: YUY2, (H, W, 2) bytes Y0 U Y1 V per pixel pair.  fmt 2: NV12, H rows of Y then H/2 rows of interleaved U V. */
+static void yuv_px(int y, int u, int v, u8 *bgr)
+{
+    const int yy = (y - 16 > 0 ? y - 16 : 0) * 1220542, uu = u - 128, vv = v - 128;
+    const int r = (yy + (1 << 19) + 1673527 * vv) >> 20;
+    const int g = (yy + (1 << 19) - 852492 * vv - 409993 * uu) >> 20;
+    const int b = (yy + (1 << 19) + 2116026 * uu) >> 20;
+    bgr[0] = (u8)(b < 0 ? 0 : b > 255 ? 255 : b); bgr[1] = (u8)(g < 0 ? 0 : g > 255 ? 255 : g);
+    bgr[2] = (u8)(r < 0 ? 0 : r > 255 ? 255 : r);
+}
+ORC_API int orc_yuv_to_bgr(const u8 *src, int fmt, int H, int W, u8 *bgr)
+{
+    if (W < 2 || (W & 1) || H < 1 || (fmt == 2 && (H & 1)) || (fmt != 1 && fmt != 2)) return -1;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x += 2) {
+            int y0, y1, u, v;
+            if (fmt == 1) {
+                const u8 *p = src + ((long)y * W + x) * 2;
+                y0 = p[0]; u = p[1]; y1 = p[2]; v = p[3];
+            } else {
+                const u8 *uv = src + (long)H * W + (long)(y / 2) * W + x;
+                y0 = src[(long)y * W + x]; y1 = src[(long)y * W + x + 1]; u = uv[0]; v = uv[1];
+            }
+            yuv_px(y0, u, v, bgr + ((long)y * W + x) * 3);
+            yuv_px(y1, u, v, bgr + ((long)y * W + x + 1) * 3);
+        }
+    return 0;
+}

@@ -367,6 +367,20 @@ def rotate(img, code):
     return out
 
 
+
+def yuv_to_bgr(src, fmt):
+    """cv2.cvtColor(src, COLOR_YUV2BGR_YUY2) for fmt 'yuy2' ((H, W, 2) u8) or COLOR_YUV2BGR_NV12 for 'nv12'
+    ((H * 3 / 2, W) u8) -> (H, W, 3) BGR.  The camera ingest step either side of the path (play_lichess.py:16-18,45)."""
+    a = _u8(src)
+    code = {"yuy2": 1, "nv12": 2}[fmt]
+    H, W = (a.shape[0], a.shape[1]) if code == 1 else (a.shape[0] * 2 // 3, a.shape[1])
+    out = np.empty((H, W, 3), np.uint8)
+    f = lib().orc_yuv_to_bgr; f.restype = C.c_int
+    if f(_p(a), C.c_int(code), C.c_int(H), C.c_int(W), _p(out)) != 0:
+        raise ValueError("yuv_to_bgr: bad shape %r for %s" % (a.shape, fmt))
+    return out
+
+
 def hough_circles(gray_u8, dp=1.2, min_dist=25, param1=100, param2=25, min_radius=0, max_radius=0, max_out=64,
                   return_info=False):
     """cv2.HoughCircles(gray, HOUGH_GRADIENT, ...) (piece_detector.py:232-241) -> (n,3) f32 (x, y, r) or None;
