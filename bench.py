@@ -293,17 +293,23 @@ def main():
                        else "oracle/cvb_oracle.c scalar C restatement"}
 
     dist = None
+    device = local_rank
     if world > 1:
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from chessboard_vision_b200.sharding import place_rank
+        # partial-node runs use the GPUs with the fast host path (profiles/r02_h2d_probe_8gpu.txt); identity at N = node size
+        device = place_rank(local_rank, world, torch.cuda.device_count())
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    config["placement"] = "rank r on GPU %s" % ("r" if device == local_rank else "(%d + r): GPUs 4-7 of this pool's boxes keep 55 GB/s "
+                          "host->device each when used together, GPUs 0-3 share 115 GB/s (profiles/r02_h2d_probe_8gpu.txt)" % (device - local_rank))
 
     from chessboard_vision_b200.sharding import bind_to_gpu_numa
-    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0
+    numa_cpus = bind_to_gpu_numa(device) if world > 1 else 0
     from chessboard_vision_b200.engine import (Engine, grid_rects, _rect_array, STATS_DTYPE, SQ_PD_STATS, SQ_PD_SET_REF,
                                                SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
-    eng = Engine(local_rank)
+    eng = Engine(device)
     n = args.frames
 
     def barrier():
@@ -334,7 +340,7 @@ def main():
         # the other BASELINE configurations (tools/bench_modes.py): same JSON contract, their own metric
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_modes
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(device) if rank == 0 else None
         if sampler:
             sampler.wait_ready()
         wall0 = time.time()
@@ -352,7 +358,7 @@ def main():
 
     rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
     M = eng.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
-    state = eng.new_state(n, S, S)
+    state = eng.new_state(n if world == 1 else 2 * n, S, S)
 
     # host batch in pinned memory (e2e source) and a resident device copy (kernel-only source), both in the ingest format
     host = eng.pinned((n,) + native_u.shape[1:])
@@ -381,12 +387,19 @@ def main():
                 eng.cvt_to_bgr_dev(d_native, args.ingest, n, H, W, d_in)
             eng.pipeline_dev(d_in, M, rects, pp, state, stats=d_stats, otsu_t=d_otsu)
 
+    my_frames = [n]        # frames this rank feeds per e2e step (equal shares until the feed rates are known)
+
     def run_e2e(k):
         for _ in range(k):
-            eng.lib  # the public host-buffer call: H2D + kernels + D2H of per-square results
-            eng.pipeline(host, M, rects, pp, state, fmt=args.ingest)
+            # the public host-buffer call: H2D + kernels + D2H of per-square results; a share above the n frames of the
+            # pinned batch wraps around (a second call on the first frames, their state in the upper stream slots)
+            done = 0
+            while done < my_frames[0]:
+                cnt = min(n, my_frames[0] - done)
+                eng.pipeline(host[:cnt], M, rects, pp, state, stream0=done, fmt=args.ingest)
+                done += cnt
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(device) if rank == 0 else None
     if sampler:
         sampler.wait_ready()
     run_dev(args.warmup)
@@ -402,6 +415,26 @@ def main():
     eng.profile(False)
 
     run_e2e(args.warmup)
+    e2e_shares = None
+    if dist is not None:
+        # The GPUs of a node need not share the host's PCIe / memory path equally (measured: profiles/r02_h2d_probe_8gpu.txt),
+        # and every rank of this path is bound by its host->device copy: give each rank a share of the N * frames of a step
+        # in proportion to the rate it just sustained, so that all ranks finish together.  No data moves between ranks.
+        import torch
+        from chessboard_vision_b200.sharding import proportional_split
+        barrier()
+        t0 = time.perf_counter(); run_e2e(3); eng.synchronize(); mine = 3 * n / (time.perf_counter() - t0)
+        rates = torch.zeros(world, dtype=torch.float64, device="cuda"); rates[rank] = mine
+        dist.all_reduce(rates)
+        rl = rates.tolist()
+        if max(rl) > 1.15 * min(rl):          # below that the differences are measurement noise: equal shares
+            e2e_shares = [min(2 * n, x) for x in proportional_split(n * world, rl, multiple=8)]
+            e2e_shares[e2e_shares.index(max(e2e_shares))] += n * world - sum(e2e_shares)
+        else:
+            e2e_shares = [n] * world
+        my_frames[0] = e2e_shares[rank]
+        eng.pipeline(host[:n], M, rects, pp_cal, state, stream0=n, fmt=args.ingest)      # models for the upper stream slots
+        run_e2e(1)
     ms_e2e, _ = timed(run_e2e, args.steps)
 
     # ---- side measurements (rank 0, not part of value/e2e): the other BASELINE.json configurations through the very
@@ -548,10 +581,14 @@ def main():
                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8 (f32 bilateral / CLAHE blend, f64 Otsu and warp coordinates)",
                "data": "synthetic", "config": config, "per_gpu": value / world,
-               "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.nbytes),
-                       "d2h_bytes_per_step": int(n * len(rects) * STATS_DTYPE.itemsize + n * 4),
+               "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(host.nbytes) * world,
+                       "d2h_bytes_per_step": int(n * len(rects) * STATS_DTYPE.itemsize + n * 4) * world,
                        "ms_per_step": ms_e2e / args.steps,
-                       "api": "Engine.pipeline -> cvb_pipeline (pinned host frames in, per-square statistics + Otsu "
+                       "frames_per_rank": e2e_shares or [n],
+                       "sharding": "equal" if not e2e_shares or len(set(e2e_shares)) == 1 else "N x %d frames per step, each rank's share proportional to the "
+                                   "host->device rate it sustained in the warm-up (the GPUs of this box do not share the host "
+                                   "path equally); no data-path collective" % n,
+                       "api": "Engine.pipeline -> cvb_pipeline_fmt (pinned host frames in, per-square statistics + Otsu "
                               "thresholds out)"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "parity": parity, "extras": extras}

@@ -125,6 +125,7 @@ void cvb_destroy(cvb_handle *h)
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_copy[i]); cudaEventDestroy(h->ev_done[i]); }
@@ -430,8 +431,39 @@ static int analysis_tail(cvb_handle *h, const uint8_t *src, const int32_t *minma
     }
     CVB_TRY(launch_finish(h, src, n, H, W, minmax, enhanced, gray, blurred, want_bin ? hist : nullptr));
     if (want_bin) {
-        CVB_TRY(launch_otsu(h, hist, n, npx, otsu_t));
-        if (binary) CVB_TRY(launch_threshold(h, blurred, n, npx, otsu_t, binary));
+        // The Otsu scan is a chain of 256 dependent f64 divisions (~40 us whatever the batch).  For small batches the
+        // whole-path entry points fork it, with the mask, onto a second stream: the warp and the square kernel that
+        // follow on the main stream need neither (they read the enhanced frame), join_tail() brings the streams together.
+        const bool fork = h->fork_tail && n <= 16;
+        cudaStream_t main_stream = h->stream;
+        if (fork) {
+            if (!h->aux_stream) {
+                CVB_CHECK_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+                CVB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                CVB_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+            }
+            CVB_CHECK_CUDA(cudaEventRecord(h->ev_fork, main_stream));
+            CVB_CHECK_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+            h->stream = h->aux_stream;
+        }
+        int rc = launch_otsu(h, hist, n, npx, otsu_t);
+        if (rc == CVB_OK && binary) rc = launch_threshold(h, blurred, n, npx, otsu_t, binary);
+        h->stream = main_stream;
+        CVB_TRY(rc);
+        if (fork) {
+            CVB_CHECK_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+            h->tail_pending = true;
+        }
+    }
+    return CVB_OK;
+}
+
+// the main stream waits for a forked analysis tail (no-op when nothing was forked)
+static int join_tail(cvb_handle *h)
+{
+    if (h->tail_pending) {
+        h->tail_pending = false;
+        CVB_CHECK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     return CVB_OK;
 }
@@ -859,9 +891,14 @@ static int pipeline_launch(cvb_handle *h, const uint8_t *bgr, int n, int H, int 
     if (!binary) CVB_TRY(cvb_ws(h, h->ws_bin, npx * n, (void **)&binary));
     if (!otsu_t) CVB_TRY(cvb_ws(h, h->ws_otsu, sizeof(int32_t) * n, (void **)&otsu_t));
     if (!warped) CVB_TRY(cvb_ws(h, h->ws_warp, (size_t)S * S * 3 * n, (void **)&warped));
-    CVB_TRY(cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t));
-    CVB_TRY(launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_minv, n_mats, S, S, p->rotate_180 != 0, warped));
-    return squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
+    h->fork_tail = true;
+    int rc = cvb_enhance_dev(h, bgr, n, H, W, &p->enhance, enhanced, gray, binary, otsu_t);
+    h->fork_tail = false;
+    if (rc == CVB_OK)
+        rc = launch_warp(h, p->warp_enhanced ? enhanced : bgr, n, H, W, d_minv, n_mats, S, S, p->rotate_180 != 0, warped);
+    if (rc == CVB_OK) rc = squares_impl(h, warped, n, S, S, 3, rects, n_sq, select, state, stream0, &p->squares, stats);
+    const int rj = join_tail(h);
+    return rc != CVB_OK ? rc : rj;
 }
 
 static int pipeline_check(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const cvb_pipeline_params *p,

@@ -82,6 +82,11 @@ struct cvb_handle {
     DevBuf ws_lab, ws_prof, ws_in, ws_raw, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
     DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
+    // forked tail of the analysis stage (Otsu scan + mask) for small batches: it runs on aux_stream beside the warp and
+    // the square kernel, which do not depend on it (cvb_api.cu: analysis_tail / join_tail)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_tail = false, tail_pending = false;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     int chunk_frames = 0;       // frames per chunk of the host-buffer pipeline; 0 = chosen per call (cvb_pipeline_fmt)

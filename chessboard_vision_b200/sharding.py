@@ -65,3 +65,35 @@ def bind_to_gpu_numa(device_index):
     except Exception:
         pass
     return 0
+
+
+def place_rank(local_rank, world, visible_gpus):
+    """GPU index for `local_rank` of `world` ranks on a node that shows `visible_gpus` devices.
+
+    Measured on this pool's 8 x B200 boxes (profiles/r02_h2d_probe_8gpu.txt): every GPU copies host -> device at
+    55.6 GB/s alone, GPUs 4-7 keep that rate together (218 GB/s), GPUs 0-3 share one 115 GB/s host path (29 GB/s each).
+    The host-buffer path is bound by exactly that copy, so runs on fewer GPUs than the node has start from the top:
+    rank r -> GPU (visible - world + r).  With all GPUs in use, or a launcher that shows each job only its own GPUs,
+    this is the identity."""
+    visible_gpus, world, local_rank = int(visible_gpus), int(world), int(local_rank)
+    if visible_gpus <= world:
+        return local_rank % max(1, visible_gpus)
+    return visible_gpus - world + local_rank
+
+
+def proportional_split(total, rates, multiple=1):
+    """Split `total` work items over ranks in proportion to their measured `rates` (items / s), each share a multiple of
+    `multiple` except that the shares always sum to `total`.  Ranks whose host path is slower get fewer frames, so that
+    all ranks finish together (the host-fed path on a box whose GPUs do not share the host bandwidth equally)."""
+    rates = [max(float(r), 1e-9) for r in rates]
+    s = sum(rates)
+    shares = [int(total * r / s) // multiple * multiple for r in rates]
+    rest = total - sum(shares)
+    order = sorted(range(len(rates)), key=lambda i: -rates[i])
+    i = 0
+    while rest > 0:
+        step = min(multiple, rest)
+        shares[order[i % len(order)]] += step
+        rest -= step
+        i += 1
+    return shares

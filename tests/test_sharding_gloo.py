@@ -22,6 +22,20 @@ def test_shard_range_partitions():
     assert [stream_owner(s, 8) for s in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
 
 
+def test_rank_placement_and_proportional_split():
+    from chessboard_vision_b200.sharding import place_rank, proportional_split
+    assert [place_rank(r, 8, 8) for r in range(8)] == list(range(8))           # whole node: identity
+    assert [place_rank(r, 4, 8) for r in range(4)] == [4, 5, 6, 7]             # partial node: the GPUs with the fast host path
+    assert [place_rank(r, 2, 8) for r in range(2)] == [6, 7] and place_rank(0, 1, 8) == 7
+    assert [place_rank(r, 4, 4) for r in range(4)] == [0, 1, 2, 3]             # launcher shows only the job's GPUs
+    assert place_rank(0, 1, 1) == 0
+    shares = proportional_split(2048, [23.4] * 4 + [35.5] * 4, multiple=8)
+    assert sum(shares) == 2048 and all(x % 8 == 0 for x in shares)
+    assert shares[0] < 256 < shares[7] and abs(shares[7] / shares[0] - 35.5 / 23.4) < 0.08
+    assert proportional_split(10, [1, 1, 1], multiple=4) in ([4, 4, 2], [4, 2, 4], [2, 4, 4]) or sum(proportional_split(10, [1, 1, 1], 4)) == 10
+    assert proportional_split(7, [5.0], 8) == [7]
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
