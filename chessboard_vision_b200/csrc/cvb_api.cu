@@ -122,6 +122,7 @@ void cvb_destroy(cvb_handle *h)
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->d_tables) cudaFree(h->d_tables);
+    if (h->wtex) cudaDestroyTextureObject(h->wtex);
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

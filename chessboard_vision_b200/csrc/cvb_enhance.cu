@@ -423,6 +423,7 @@ struct FusedArgs {
     float sw[81];             // spatial weights [dy+4][dx+4] (used when !FOLD)
     int32_t *minmax;          // per frame {min,max} or null
     int src_is_lab;           // LIGHT: src already holds (L, a, b) bytes (stored by the tile-histogram pass)
+    cudaTextureObject_t wtex; // the [10][768] weight table as a 1-D texture (TEXMODE != 0)
 };
 
 // class of a tap by squared radius: 0,1,2,4,5,8,9,10,13,16 -> 0..9
@@ -472,8 +473,12 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
 #ifndef CONV_PAIR
 #define CONV_PAIR 1
 #endif
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
-__global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
+// TEXMODE: which bilateral taps fetch their weight through the texture unit (tex1Dfetch on the same [10][768] table)
+// instead of the shared-memory copy: 0 none, 1 all, 2 every second tap, 3 one tap in three.  A texture fetch takes
+// the colour distance as its index directly (no address arithmetic) and runs on the TEX pipe, which the kernel does
+// not use otherwise, so it unloads the shared-memory pipe, where the lookups average 2.5 wavefronts.
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1, int TEXMODE = 0>
+__global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
@@ -632,6 +637,11 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
                                 w = 1.0f;      // the centre tap: distance 0 in space and colour, exp(0) * exp(0)
                             } else {
                                 const unsigned sad = __vsadu4(px[c], ctr[t][j]);
+                                constexpr bool kAll = TEXMODE == 1;
+                                const int tapno = (dy + 4) * 9 + dx + 4 + j;
+                                const bool via_tex = LUTMODE == 1 && (kAll || (TEXMODE == 2 && (tapno & 1)) || (TEXMODE == 3 && tapno % 3 == 0));
+                                if (via_tex) w = tex1Dfetch<float>(a.wtex, (int)(sad + r2_class(dy * dy + dx * dx) * 768));
+                                else
                                 w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
                                                  : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
                             }
@@ -812,11 +822,11 @@ __global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
     }
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1, int TEXMODE = 0>
 static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
-    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS, TEXMODE>;
     // per device: one handle per GPU, possibly several GPUs in one process
     if (!h->fused_attr_done.count((const void *)kern)) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
@@ -836,7 +846,7 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     FusedArgs a;
     a.src_is_lab = src_is_lab ? 1 : 0;
     a.src = src; a.dst = out; a.H = H; a.W = W; a.tabs = h->d_tables; a.lut = lut; a.minmax = minmax;
-    a.wlut = nullptr;
+    a.wlut = nullptr; a.wtex = 0;
     if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
     if (bilateral) {
         if (h->color_sigma != sigma_color || h->space_sigma != sigma_space || !h->d_color) {
@@ -858,8 +868,19 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
             CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
             CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // pageable source dies at scope end
             h->color_sigma = sigma_color; h->space_sigma = sigma_space;
+            if (!h->wtex) {
+                cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
+                rd.resType = cudaResourceTypeLinear;
+                rd.res.linear.devPtr = h->d_color;
+                rd.res.linear.desc = cudaCreateChannelDesc<float>();
+                rd.res.linear.sizeInBytes = 10 * 768 * sizeof(float);
+                cudaTextureDesc td; memset(&td, 0, sizeof td);
+                td.readMode = cudaReadModeElementType;
+                CVB_CHECK_CUDA(cudaCreateTextureObject(&h->wtex, &rd, &td, nullptr));
+            }
         }
         a.wlut = h->d_color;
+        a.wtex = h->wtex;
     }
     memset(a.sw, 0, sizeof a.sw);
     if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);

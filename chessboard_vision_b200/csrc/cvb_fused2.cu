@@ -521,6 +521,249 @@ __global__ void __launch_bounds__(NG * NTG, 1) k_fused_tma(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Producer / consumer form: NP lighting threads run one tile ahead of NQ bilateral + sharpen threads.
+//   producers: wait for the Lab tile (TMA) -> patch the mirror ring -> lighting into sA[k & 1] -> signal `full`
+//              -> start the TMA load of their next tile;
+//   consumers: wait `full` -> bilateral from sA[k & 1] into sB -> signal `empty` -> sharpen + store + min/max.
+// The two stages are bound by different pipes (lighting: integer pipe and global-load latency; bilateral: FMA and
+// shared-memory pipes), so running them side by side on one SM lets their pipe demands overlap the way two resident
+// CTAs of k_fused do -- with ONE lane-private weight table instead of two conflict-ridden folded ones.
+// ---------------------------------------------------------------------------------------------------------------
+template <int TH, bool LUTP>
+struct SmemPC {
+    static constexpr int BH = TH + 2 * BY, AH = BH + 2 * AR;
+    static constexpr size_t rawBytes = (size_t)RAW_PITCH * AH;
+    static constexpr size_t offRaw = 0;
+    static constexpr size_t offA0 = (rawBytes + 127) / 128 * 128;
+    static constexpr size_t aBytes = (size_t)AW * AH * 4;
+    static constexpr size_t offB = offA0 + 2 * aBytes;
+    static constexpr size_t offX = offB + (size_t)BW * BH * 4;
+    static constexpr size_t offW = (offX + (size_t)(AW + AH) * sizeof(Axis2) + 15) / 16 * 16;
+    static constexpr size_t offT = offW + (LUTP ? 768 * 32 * 4 : 10 * 768 * 4);
+    static constexpr size_t offBar = offT + sizeof(SmemColorTables);
+    static constexpr size_t bytes = offBar + 8 * sizeof(uint64_t);
+    static_assert(offA0 % 16 == 0 && aBytes % 16 == 0 && offB % 16 == 0 && offX % 16 == 0 && offT % 16 == 0 && offBar % 8 == 0, "alignment");
+    static_assert(bytes <= 232448, "more than 227 KB of shared memory");
+};
+
+// wait that does not burn issue slots: the spinning warps of the producer / consumer kernel otherwise execute 10 % of
+// all instructions (ncu: BRA / SYNCS / YIELD), on a kernel that is bound by instruction issue
+CVB_DEV void mbar_wait_sleep(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITS_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x400;\n"
+        "@p bra DONES_%=;\n"
+        "nanosleep.u32 256;\n"
+        "bra WAITS_%=;\n"
+        "DONES_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(phase)
+        : "memory");
+}
+CVB_DEV void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+template <int COUNT>
+CVB_DEV void named_sync(int id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+
+template <int TH, int NP, int NQ, bool LUTP, int ACC>
+__global__ void __launch_bounds__(NP + NQ, 1) k_fused_pc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Fused2Args a)
+{
+    using S = SmemPC<TH, LUTP>;
+    constexpr int BH = S::BH, AH = S::AH, NT = NP + NQ;
+    constexpr int ITEMS_B = (BH / 2) * RUNS;
+    static_assert(BH % 2 == 0 && NP % 32 == 0 && NQ % 32 == 0, "whole warps, row pairs");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sRaw = smem + S::offRaw;
+    uint32_t *sB = reinterpret_cast<uint32_t *>(smem + S::offB);
+    Axis2 *sAx = reinterpret_cast<Axis2 *>(smem + S::offX);
+    float *sW = reinterpret_cast<float *>(smem + S::offW);
+    SmemColorTables *sTab = reinterpret_cast<SmemColorTables *>(smem + S::offT);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::offBar);   // 0 tables, 1 folded weights, 2 raw tile, 3-4 full, 5-6 empty
+    uint64_t *bar_raw = &bars[2], *bar_full = &bars[3], *bar_empty = &bars[5];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int H = a.H, W = a.W;
+    const bool producer = tid < NP;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(bar_raw, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_full[b], NP / 32); mbar_init(&bar_empty[b], NQ / 32); }
+        mbar_init_fence();
+        bulk_g2s(sTab, a.tabs, (uint32_t)sizeof(SmemColorTables), &bars[0]);
+        if (!LUTP) bulk_g2s(sW, a.wlut, 10 * 768 * 4, &bars[1]);
+    }
+    if (LUTP) {
+        const float *col = a.wlut + 10 * 768;
+        for (int k = tid; k < 768 * 32; k += NT) sW[k] = __ldg(col + (k >> 5));
+    }
+    __syncthreads();
+    mbar_wait(&bars[0], 0);
+    if (!LUTP) mbar_wait(&bars[1], 0);
+
+    if (producer) {
+        // ------------------------------------------------ lighting warps ------------------------------------------------
+        int t = blockIdx.x;
+        if (t >= a.total_tiles) return;
+        TilePos<TH> cur = tile_pos<TH>(t, a);
+        fill_axis<NP, AH>(sAx, a, cur.x0, cur.y0, tid);
+        if (tid == 0) tma_load_tile(sRaw, &tmap, raw_c0(cur.x0), cur.y0 - BY - AR, cur.frame, bar_raw, (uint32_t)S::rawBytes);
+        named_sync<NP>(1);
+        for (int k = 0; t < a.total_tiles; t += gridDim.x, ++k) {
+            const int x0 = cur.x0, y0 = cur.y0, frame = cur.frame;
+            const int ax0 = x0 - BX - AR, ay0 = y0 - BY - AR;
+            const int tn = t + gridDim.x;
+            const bool has_next = tn < a.total_tiles;
+            TilePos<TH> nxt = cur;
+            if (has_next) nxt = tile_pos<TH>(tn, a);
+            uint32_t *sA = reinterpret_cast<uint32_t *>(smem + S::offA0 + (size_t)(k & 1) * S::aBytes);
+            mbar_wait_sleep(bar_raw, k & 1);
+            uint8_t *raw = sRaw + raw_lead(x0);
+            if (ax0 < 0 || ay0 < 0 || ax0 + AW > W || ay0 + AH > H) {
+                const int top_n = max(0, min(AH, -ay0)), bot0 = max(0, min(AH, H - ay0));
+                const int left_n = max(0, min(AW, -ax0)), right0 = max(0, min(AW, W - ax0));
+                const int ring_rows = top_n + (AH - bot0), ring_cols = left_n + (AW - right0);
+                for (int i = tid; i < ring_rows * AW + (AH - ring_rows) * ring_cols; i += NP) {
+                    int ly, lx;
+                    if (i < ring_rows * AW) {
+                        const int r = i / AW;
+                        lx = i - r * AW; ly = r < top_n ? r : bot0 + (r - top_n);
+                    } else {
+                        const int k2 = i - ring_rows * AW, r = k2 / ring_cols, c = k2 - r * ring_cols;
+                        ly = top_n + r; lx = c < left_n ? c : right0 + (c - left_n);
+                    }
+                    const int x = ax0 + lx, y = ay0 + ly;
+                    if (x < -6 || x > W + 5 || y < -5 || y > H + 5) continue;
+                    const int sx = reflect101(x, W) - ax0, sy = reflect101(y, H) - ay0;
+                    if (sx < 0 || sx >= AW || sy < 0 || sy >= AH) continue;
+                    const uint8_t *s = raw + sy * RAW_PITCH + sx * 3;
+                    uint8_t *d = raw + ly * RAW_PITCH + lx * 3;
+                    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+                }
+                named_sync<NP>(1);
+            }
+            mbar_wait_sleep(&bar_empty[k & 1], ((k >> 1) & 1) ^ 1);        // the consumers are done with this buffer's previous tile
+            {
+                const uint8_t *lut = a.lut + (size_t)frame * a.g.tiles_x * a.g.tiles_y * 256;
+                constexpr int PAIRS = AW / 2;
+                for (int item = tid; item < AH * PAIRS; item += NP) {
+                    const int ly = item / PAIRS, lx = 2 * (item - ly * PAIRS);
+                    const uint16_t *rp = reinterpret_cast<const uint16_t *>(raw + ly * RAW_PITCH + lx * 3);
+                    const uint32_t u0 = rp[0], u1 = rp[1], u2 = rp[2];
+                    const Axis2 cy = sAx[AW + ly], c0 = sAx[lx], c1 = sAx[lx + 1];
+                    const uint32_t q0 = light_px(sTab, lut, c0, cy, u0 & 0xff, u0 >> 8, u1 & 0xff);
+                    const uint32_t q1 = light_px(sTab, lut, c1, cy, u1 >> 8, u2 & 0xff, u2 >> 8);
+                    *reinterpret_cast<uint2 *>(sA + ly * AW + lx) = make_uint2(q0, q1);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[k & 1]);
+            named_sync<NP>(1);                       // every producer is done with the raw tile and the axis records
+            if (has_next) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tma_load_tile(sRaw, &tmap, raw_c0(nxt.x0), nxt.y0 - BY - AR, nxt.frame, bar_raw, (uint32_t)S::rawBytes);
+                }
+                fill_axis<NP, AH>(sAx, a, nxt.x0, nxt.y0, tid);
+                named_sync<NP>(1);
+            }
+            cur = nxt;
+        }
+    } else {
+        // ------------------------------------------- bilateral + sharpen warps -------------------------------------------
+        const int ctid = tid - NP;
+        const float *myW = sW + lane;
+        int t = blockIdx.x;
+        for (int k = 0; t < a.total_tiles; t += gridDim.x, ++k) {
+            const TilePos<TH> cur = tile_pos<TH>(t, a);
+            const int x0 = cur.x0, y0 = cur.y0, frame = cur.frame;
+            const int bx0 = x0 - BX, by0 = y0 - BY;
+            const uint32_t *sA = reinterpret_cast<const uint32_t *>(smem + S::offA0 + (size_t)(k & 1) * S::aBytes);
+            mbar_wait_sleep(&bar_full[k & 1], (k >> 1) & 1);
+            for (int item = ctid; item < ITEMS_B; item += NQ) {
+                const int rg = item / RUNS, r4 = (item - rg * RUNS) * 4;
+                const int row0 = rg * 2;
+                const int Y0 = by0 + row0, X = bx0 + r4;
+                if (Y0 + 1 < 0 || Y0 >= H || X + 3 < 0 || X >= W) continue;
+                if (ACC == 2) bilateral_item_packed<LUTP>(sA, sB, sW, myW, a, row0, r4);
+                else bilateral_item_scalar<LUTP>(sA, sB, sW, myW, a, row0, r4);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[k & 1]);     // this warp no longer reads the lighting tile
+            named_sync<NQ>(2);                                 // sB complete
+            {
+                const int vh = min(TH, H - y0), vw = min(TW, W - x0);
+                const bool top = y0 == 0, bottom = y0 + vh == H, left = x0 == 0, right = x0 + vw == W;
+                if (top || bottom) {
+                    for (int i = ctid; i < BW; i += NQ) {
+                        if (top) sB[(BY - 1) * BW + i] = sB[(BY + 1) * BW + i];
+                        if (bottom) sB[(BY + vh) * BW + i] = sB[(BY + vh - 2) * BW + i];
+                    }
+                    named_sync<NQ>(2);
+                }
+                if (left || right) {
+                    for (int i = ctid; i < vh + 2; i += NQ) {
+                        uint32_t *row = sB + (BY - 1 + i) * BW;
+                        if (left) row[BX - 1] = row[BX + 1];
+                        if (right) row[BX + vw] = row[BX + vw - 2];
+                    }
+                    named_sync<NQ>(2);
+                }
+                uint8_t *out = a.dst + (size_t)frame * H * W * 3;
+                constexpr int GROUPS = TW / 4;
+                int vmin = 255, vmax = 0;
+                for (int item = ctid; item < TH * GROUPS; item += NQ) {
+                    const int ty = item / GROUPS, tx4 = (item - ty * GROUPS) * 4;
+                    if (ty >= vh) break;
+                    if (tx4 >= vw) continue;
+                    uint32_t cbr[6], cg[6], ctr_w[4];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) cbr[q] = cg[q] = 0;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const uint32_t *rp = sB + (ty + BY - 1 + r) * BW + tx4;
+                        const uint4 q0 = *reinterpret_cast<const uint4 *>(rp), q1 = *reinterpret_cast<const uint4 *>(rp + 4);
+                        const uint32_t w[6] = {q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { cbr[q] += w[q] & 0x00ff00ffu; cg[q] += (w[q] >> 8) & 0xffu; }
+                        if (r == 1) { ctr_w[0] = w[1]; ctr_w[1] = w[2]; ctr_w[2] = w[3]; ctr_w[3] = w[4]; }
+                    }
+                    uint32_t res[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t s02 = cbr[j] + cbr[j + 1] + cbr[j + 2], s1 = cg[j] + cg[j + 1] + cg[j + 2];
+                        const uint32_t c = ctr_w[j];
+                        const int b = clamp_u8(10 * (int)(c & 0xff) - (int)(s02 & 0xffff));
+                        const int g = clamp_u8(10 * (int)((c >> 8) & 0xff) - (int)s1);
+                        const int r = clamp_u8(10 * (int)((c >> 16) & 0xff) - (int)(s02 >> 16));
+                        res[j] = pack_bgr(b, g, r);
+                        vmin = min(vmin, min(b, min(g, r)));
+                        vmax = max(vmax, max(b, max(g, r)));
+                    }
+                    uint32_t *o32 = reinterpret_cast<uint32_t *>(out + ((size_t)(y0 + ty) * W + x0 + tx4) * 3);
+                    o32[0] = (res[0] & 0xffffffu) | (res[1] << 24);
+                    o32[1] = ((res[1] >> 8) & 0xffffu) | (res[2] << 16);
+                    o32[2] = ((res[2] >> 16) & 0xffu) | (res[3] << 8);
+                }
+                if (a.minmax) {
+                    vmin = warp_min(vmin); vmax = warp_max(vmax);
+                    if (lane == 0 && vmin <= vmax) {
+                        atomicMin(a.minmax + 2 * frame, vmin);
+                        atomicMax(a.minmax + 2 * frame + 1, vmax);
+                    }
+                }
+            }
+            named_sync<NQ>(2);                                 // sB free for the bilateral stage of the next tile
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -569,6 +812,29 @@ int launch_variant(cvb_handle *h, const uint8_t *lab, Fused2Args &a)
     return CVB_OK;
 }
 
+template <int TH, int NP, int NQ, bool LUTP, int ACC>
+int launch_pc(cvb_handle *h, const uint8_t *lab, Fused2Args &a)
+{
+    using S = SmemPC<TH, LUTP>;
+    static_assert(((TH + 2 * BY) / 2) * RUNS <= NQ, "one bilateral item per consumer thread");
+    auto kern = k_fused_pc<TH, NP, NQ, LUTP, ACC>;
+    if (!h->fused_attr_done.count((const void *)kern)) {
+        CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+        h->fused_attr_done.insert((const void *)kern);
+    }
+    a.tiles_x = (a.W + TW - 1) / TW; a.tiles_y = (a.H + TH - 1) / TH;
+    const long total = (long)a.tiles_x * a.tiles_y * a.n;
+    CVB_REQUIRE(total < (1l << 31), "too many tiles");
+    a.total_tiles = (int)total;
+    alignas(64) CUtensorMap map;
+    CVB_TRY(make_lab_tensor_map(lab, a.n, a.H, a.W, S::AH, &map));
+    const int grid = (int)std::min<long>(total, h->sm_count);
+    PROF(h, "k_fused");
+    kern<<<grid, NP + NQ, S::bytes, h->stream>>>(map, a);
+    LAUNCH_CHECK(h);
+    return CVB_OK;
+}
+
 }  // namespace
 
 bool fused_tma_applicable(int H, int W, const uint8_t *lab, const uint8_t *out)
@@ -593,13 +859,12 @@ int launch_fused_tma(cvb_handle *h, const uint8_t *lab, int n, int H, int W, con
         }
         a.sws[dy + 4] = (nt & 1) ? space81[(dy + 4) * 9 + tap_dx(dy, nt - 1) + 4] : 0.f;
     }
+    // the variants that stay built (every one bit-identical to the oracle; times in profiles/r02_notes.md, where the
+    // results of the variants that were measured and dropped are kept too)
     switch (variant) {
-    case 1: return launch_variant<1, 1024, 64, false, 2>(h, lab, a);   // folded table, packed, one group
-    case 2: return launch_variant<1, 512, 64, true, 2>(h, lab, a);     // private table, packed, one group of 512
-    case 3: return launch_variant<1, 1024, 64, true, 2>(h, lab, a);    // private table, packed, one group of 1024
-    case 4: return launch_variant<2, 512, 30, true, 2>(h, lab, a);     // two groups, 120 x 30 tiles, packed
-    case 5: return launch_variant<1, 1024, 64, true, 0>(h, lab, a);    // private table, scalar, one group of 1024
-    case 6: return launch_variant<1, 512, 64, true, 0>(h, lab, a);     // private table, scalar, one group of 512
-    default: return launch_variant<2, 512, 30, true, 0>(h, lab, a);    // two groups, 120 x 30 tiles, scalar
+    case 1: return launch_variant<1, 1024, 64, false, 2>(h, lab, a);   // one group of 1024, folded table, packed accumulation
+    case 2: return launch_variant<1, 512, 64, true, 2>(h, lab, a);     // one group of 512, private table, packed
+    case 3: return launch_variant<2, 512, 30, true, 0>(h, lab, a);     // two groups of 512 on 120 x 30 tiles, private table, scalar
+    default: return launch_pc<46, 256, 768, true, 0>(h, lab, a);       // producer / consumer warps, 120 x 46 tiles, private table
     }
 }

@@ -77,6 +77,7 @@ struct cvb_handle {
     CvbTables *d_tables = nullptr;
     // bilateral colour LUT cache (device) keyed by sigma_color
     float *d_color = nullptr;
+    cudaTextureObject_t wtex = 0;      // the folded weight table as a 1-D texture (experiments with texture-unit lookups)
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
     DevBuf ws_lab, ws_prof, ws_in, ws_raw, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
