@@ -152,6 +152,7 @@ SYMBOLS = [
                               _P, _P, _P, _P, _P, _P]),
     ("cvb_set_chunk_frames", _I, [_P, _I]),
     ("cvb_pipeline", _I, [_P, _P, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    ("cvb_debug_bounds_violations", C.c_longlong, [_P, C.POINTER(_I)]),
     ("cvb_frame_bytes", _SZ, [_I, _I, _I]),
     ("cvb_cvt_to_bgr_dev", _I, [_P, _P, _I, _I, _I, _I, _P]),
     ("cvb_pipeline_fmt", _I, [_P, _P, _I, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
@@ -165,11 +166,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = LIB_PATH      # CVB200_LIB=<...>/libcvb200_dbg.so selects the debug build (index checks, make debug)
+    if not os.path.exists(path):
         raise ImportError(
             "libcvb200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a). chessboard_vision_b200 has no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "(nvcc, sm_100a). chessboard_vision_b200 has no CPU fallback." % path)
+    lib = C.CDLL(path)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the .so is stale
         fn.restype = res

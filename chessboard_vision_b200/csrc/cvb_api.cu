@@ -122,7 +122,6 @@ void cvb_destroy(cvb_handle *h)
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (h->d_tables) cudaFree(h->d_tables);
-    if (h->wtex) cudaDestroyTextureObject(h->wtex);
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1041,6 +1040,28 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const c
                  int32_t *otsu_t, cvb_square_stats *stats)
 {
     return cvb_pipeline_fmt(h, bgr, CVB_FMT_BGR, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, otsu_t, stats);
+}
+
+// sum of the index-check counters of the debug build (cvb_device.cuh); -1 in the release build, which has no checks
+long long cvb_debug_bounds_violations(cvb_handle *h, int *first_line)
+{
+    if (first_line) *first_line = 0;
+#ifdef CVB_DEBUG_BOUNDS
+    if (!h || cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -2;
+    void (*tus[])(unsigned long long *, int *) = {cvb_bounds_enhance, cvb_bounds_fused2, cvb_bounds_grid, cvb_bounds_canny,
+                                                  cvb_bounds_hough, cvb_bounds_ingest};
+    unsigned long long total = 0;
+    for (auto fn : tus) {
+        unsigned long long n = 0; int line = 0;
+        fn(&n, &line);
+        if (n && first_line && !*first_line) *first_line = line;
+        total += n;
+    }
+    return (long long)total;
+#else
+    (void)h;
+    return -1;
+#endif
 }
 
 int cvb_set_chunk_frames(cvb_handle *h, int frames)

@@ -213,3 +213,5 @@ int launch_projections(cvb_handle *h, const uint8_t *plane, int n, int H, int W,
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
+
+CVB_BOUNDS_TU(canny)

@@ -4,6 +4,32 @@
 
 #define CVB_DEV __device__ __forceinline__
 
+// ---- index checks of the debug build (make debug -> libcvb200_dbg.so, -DCVB_DEBUG_BOUNDS) ---------------------------
+// compute-sanitizer is closed on this pool, so the shared-memory tile / halo indices and the global offsets of the
+// tiled kernels carry explicit range checks in a debug build: a violation bumps a per-translation-unit counter (and
+// records its source line) instead of trapping, cvb_debug_bounds_violations() sums the counters, and
+// tests/test_gpu_debug_bounds.py runs the odd-size whole-path script on that library and expects zero.
+#ifdef CVB_DEBUG_BOUNDS
+static __device__ unsigned long long cvb_bounds_fail_ctr;
+static __device__ int cvb_bounds_first_line;
+#define CVB_BOUNDS(cond)                                                                          \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            if (atomicAdd(&cvb_bounds_fail_ctr, 1ull) == 0ull) cvb_bounds_first_line = __LINE__;  \
+        }                                                                                         \
+    } while (0)
+#define CVB_BOUNDS_TU(name)                                                                       \
+    void cvb_bounds_##name(unsigned long long *n, int *line)                                      \
+    {                                                                                             \
+        *n = 0; *line = 0;                                                                        \
+        cudaMemcpyFromSymbol(n, cvb_bounds_fail_ctr, sizeof *n);                                  \
+        cudaMemcpyFromSymbol(line, cvb_bounds_first_line, sizeof *line);                          \
+    }
+#else
+#define CVB_BOUNDS(cond) ((void)0)
+#define CVB_BOUNDS_TU(name) void cvb_bounds_##name(unsigned long long *n, int *line) { *n = 0; *line = 0; }
+#endif
+
 // cv::borderInterpolate(BORDER_REFLECT_101)
 CVB_DEV int reflect101(int p, int n)
 {

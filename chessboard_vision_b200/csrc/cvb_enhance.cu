@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *__restrict__ s
         const int L = (296 * fY - 1336934 + 16384) >> 15;                    // never saturate (tests/test_abi.py)
         const int A = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
         const int Bc = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+        CVB_BOUNDS(L >= 0 && L < 256 && A >= 0 && A < 256 && Bc >= 0 && Bc < 256);
         atomicAdd(&my[L], 1);
         return pack_bgr(L, A, Bc);
     };
@@ -423,7 +424,6 @@ struct FusedArgs {
     float sw[81];             // spatial weights [dy+4][dx+4] (used when !FOLD)
     int32_t *minmax;          // per frame {min,max} or null
     int src_is_lab;           // LIGHT: src already holds (L, a, b) bytes (stored by the tile-histogram pass)
-    cudaTextureObject_t wtex; // the [10][768] weight table as a 1-D texture (TEXMODE != 0)
 };
 
 // class of a tap by squared radius: 0,1,2,4,5,8,9,10,13,16 -> 0..9
@@ -473,12 +473,11 @@ CVB_DEV float byte_to_float(uint32_t q, int k)
 #ifndef CONV_PAIR
 #define CONV_PAIR 1
 #endif
-// TEXMODE: which bilateral taps fetch their weight through the texture unit (tex1Dfetch on the same [10][768] table)
-// instead of the shared-memory copy: 0 none, 1 all, 2 every second tap, 3 one tap in three.  A texture fetch takes
-// the colour distance as its index directly (no address arithmetic) and runs on the TEX pipe, which the kernel does
-// not use otherwise, so it unloads the shared-memory pipe, where the lookups average 2.5 wavefronts.
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1, int TEXMODE = 0>
-__global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a)
+// (Fetching the weights through the texture unit instead -- tex1Dfetch on the same table, no address arithmetic, a pipe
+// the kernel does not use otherwise -- was measured and dropped: 123 / 65 / 54 us per frame with all / half / a third of
+// the taps, the TEX pipe delivers about 4 texels per clock and SM: profiles/r02_notes.md.)
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
+__global__ void __launch_bounds__(NT) k_fused(const FusedArgs a)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
     constexpr int AW = Cfg::AW, AH = Cfg::AH, BW = Cfg::BW, BH = Cfg::BH, AR = Cfg::AR;
@@ -559,6 +558,7 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
             } else {
                 q = pack_bgr(c0, c1, c2);
             }
+            CVB_BOUNDS(i >= 0 && (size_t)i < (size_t)AW * AH && (size_t)(cy.src + cx.src) + 2 < (size_t)H * W * 3);
             sA[i] = q;
         }
     }
@@ -580,6 +580,7 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
             uint32_t ctr[ROWS][4];
 #pragma unroll
             for (int t = 0; t < ROWS; ++t) {
+                CVB_BOUNDS((row0 + t + 4) * AW + r4 + 4 + 3 < AW * AH && row0 >= 0 && r4 >= 0);
                 const uint4 c = *reinterpret_cast<const uint4 *>(sA + (row0 + t + 4) * AW + r4 + 4);
                 ctr[t][0] = c.x; ctr[t][1] = c.y; ctr[t][2] = c.z; ctr[t][3] = c.w;
 #pragma unroll
@@ -601,6 +602,7 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
                     if (v != 1 && lo >= 4) continue;                 // |dy| == 4 needs only the middle quad
+                    CVB_BOUNDS((row0 + k) * AW + r4 + 4 * v + 3 < AW * AH);
                     const uint4 q = *reinterpret_cast<const uint4 *>(rowp + 4 * v);
                     px[4 * v] = q.x; px[4 * v + 1] = q.y; px[4 * v + 2] = q.z; px[4 * v + 3] = q.w;
                 }
@@ -637,11 +639,7 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
                                 w = 1.0f;      // the centre tap: distance 0 in space and colour, exp(0) * exp(0)
                             } else {
                                 const unsigned sad = __vsadu4(px[c], ctr[t][j]);
-                                constexpr bool kAll = TEXMODE == 1;
-                                const int tapno = (dy + 4) * 9 + dx + 4 + j;
-                                const bool via_tex = LUTMODE == 1 && (kAll || (TEXMODE == 2 && (tapno & 1)) || (TEXMODE == 3 && tapno % 3 == 0));
-                                if (via_tex) w = tex1Dfetch<float>(a.wtex, (int)(sad + r2_class(dy * dy + dx * dx) * 768));
-                                else
+                                CVB_BOUNDS(sad < 768u);
                                 w = LUTMODE == 1 ? sW[r2_class(dy * dy + dx * dx) * 768 + sad]
                                                  : __fmul_rn(a.sw[(dy + 4) * 9 + dx + 4], sW[sad]);
                             }
@@ -663,6 +661,7 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
                     op[j] = pack_bgr(round_u8(__fmul_rn(sb[t][j], inv)), round_u8(__fmul_rn(sg[t][j], inv)),
                                      round_u8(__fmul_rn(sr[t][j], inv)));
                 }
+                CVB_BOUNDS((row0 + t) * BW + r4 + 3 < BW * BH);
                 *reinterpret_cast<uint4 *>(sB + (row0 + t) * BW + r4) = o;
             }
         }
@@ -707,12 +706,14 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const uint32_t *rp = sB + (ty + BY - 1 + r) * BW + tx4;
+                CVB_BOUNDS((ty + BY - 1 + r) >= 0 && (ty + BY - 1 + r) * BW + tx4 + 7 < BW * BH);
                 const uint4 q0 = *reinterpret_cast<const uint4 *>(rp), q1 = *reinterpret_cast<const uint4 *>(rp + 4);
                 const uint32_t w[6] = {q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};      // image x - 1 .. x + 4
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { cbr[k] += w[k] & 0x00ff00ffu; cg[k] += (w[k] >> 8) & 0xffu; }
                 if (r == 1) { ctr_w[0] = w[1]; ctr_w[1] = w[2]; ctr_w[2] = w[3]; ctr_w[3] = w[4]; }
             }
+            CVB_BOUNDS(y0 + ty < H && x0 + tx4 + 3 < W);
             uint32_t res[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -822,11 +823,11 @@ __global__ void __launch_bounds__(NT, TEXMODE ? 2 : 1) k_fused(const FusedArgs a
     }
 }
 
-template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1, int TEXMODE = 0>
+template <int TW, int TH, bool LIGHT, bool BIL, bool SHARP, int NT = 256, int LUTMODE = 1, int ROWS = 1>
 static int launch_fused_t(cvb_handle *h, const FusedArgs &a, int n)
 {
     using Cfg = FusedCfg<TW, TH, LIGHT, BIL, SHARP, LUTMODE>;
-    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS, TEXMODE>;
+    auto kern = k_fused<TW, TH, LIGHT, BIL, SHARP, NT, LUTMODE, ROWS>;
     // per device: one handle per GPU, possibly several GPUs in one process
     if (!h->fused_attr_done.count((const void *)kern)) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes));
@@ -846,7 +847,7 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
     FusedArgs a;
     a.src_is_lab = src_is_lab ? 1 : 0;
     a.src = src; a.dst = out; a.H = H; a.W = W; a.tabs = h->d_tables; a.lut = lut; a.minmax = minmax;
-    a.wlut = nullptr; a.wtex = 0;
+    a.wlut = nullptr;
     if (g) a.g = *g; else memset(&a.g, 0, sizeof a.g);
     if (bilateral) {
         if (h->color_sigma != sigma_color || h->space_sigma != sigma_space || !h->d_color) {
@@ -868,19 +869,8 @@ int launch_fused(cvb_handle *h, const uint8_t *src, int n, int H, int W, bool li
             CVB_CHECK_CUDA(cudaMemcpyAsync(h->d_color, wl.data(), wl.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
             CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));   // pageable source dies at scope end
             h->color_sigma = sigma_color; h->space_sigma = sigma_space;
-            if (!h->wtex) {
-                cudaResourceDesc rd; memset(&rd, 0, sizeof rd);
-                rd.resType = cudaResourceTypeLinear;
-                rd.res.linear.devPtr = h->d_color;
-                rd.res.linear.desc = cudaCreateChannelDesc<float>();
-                rd.res.linear.sizeInBytes = 10 * 768 * sizeof(float);
-                cudaTextureDesc td; memset(&td, 0, sizeof td);
-                td.readMode = cudaReadModeElementType;
-                CVB_CHECK_CUDA(cudaCreateTextureObject(&h->wtex, &rd, &td, nullptr));
-            }
         }
         a.wlut = h->d_color;
-        a.wtex = h->wtex;
     }
     memset(a.sw, 0, sizeof a.sw);
     if (bilateral) cvb_host_bilateral_tables(sigma_color, sigma_space, nullptr, a.sw);
@@ -1127,6 +1117,7 @@ __global__ void __launch_bounds__(256, 6) k_finish(const uint8_t *__restrict__ s
                 if (enhanced) { e32[it * 8 * row32] = w0; e32[it * 8 * row32 + 1] = w1; e32[it * 8 * row32 + 2] = w2; }
                 if (gray) g32[it * 8 * grow32] = gpack;
             }
+            CVB_BOUNDS(ly >= 0 && ly < GH && 4 * lane + 3 < SW);
             *reinterpret_cast<uint32_t *>(&s_g[ly][4 * lane]) = gpack;
         }
     }
@@ -1229,6 +1220,7 @@ __global__ void __launch_bounds__(256, 6) k_finish(const uint8_t *__restrict__ s
                 const uint2 r2 = *reinterpret_cast<const uint2 *>(hrow + 2 * FW);
                 const uint2 r3 = *reinterpret_cast<const uint2 *>(hrow + 3 * FW);
                 const uint2 r4 = *reinterpret_cast<const uint2 *>(hrow + 4 * FW);
+                CVB_BOUNDS(ly + 4 < GH && x + 3 < FW && y0 + ly < H && (FAST ? Xo + 3 < W : Xo < W));
                 // two 16-bit lanes per word; each lane's sum is <= 255*256 = 65280, so no carry crosses lanes
                 const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x;
                 const uint32_t hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
@@ -1374,3 +1366,5 @@ int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const i
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
+
+CVB_BOUNDS_TU(enhance)

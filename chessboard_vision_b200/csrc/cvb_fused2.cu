@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(NG * NTG, 1) k_fused_tma(const __grid_constant
                 if (sx < 0 || sx >= AW || sy < 0 || sy >= AH) continue;
                 const uint8_t *s = raw + sy * RAW_PITCH + sx * 3;
                 uint8_t *d = raw + ly * RAW_PITCH + lx * 3;
+                CVB_BOUNDS(ly >= 0 && ly < AH && lx >= 0 && lx < AW && (d - sRaw) + 2 < (int)S::rawBytes && (s - sRaw) + 2 < (int)S::rawBytes);
                 d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
             }
             group_sync<NG, NTG>(group);
@@ -426,6 +427,7 @@ __global__ void __launch_bounds__(NG * NTG, 1) k_fused_tma(const __grid_constant
             for (int item = tid; item < AH * PAIRS; item += NTG) {
                 const int ly = item / PAIRS, lx = 2 * (item - ly * PAIRS);
                 const uint16_t *rp = reinterpret_cast<const uint16_t *>(raw + ly * RAW_PITCH + lx * 3);
+                CVB_BOUNDS(ly < AH && lx + 1 < AW && (raw - sRaw) + ly * RAW_PITCH + lx * 3 + 5 < (int)S::rawBytes);
                 const uint32_t u0 = rp[0], u1 = rp[1], u2 = rp[2];                    // L0 a0 | b0 L1 | a1 b1
                 const Axis2 cy = sAx[AW + ly], c0 = sAx[lx], c1 = sAx[lx + 1];
                 const uint32_t q0 = light_px(sTab, lut, c0, cy, u0 & 0xff, u0 >> 8, u1 & 0xff);
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(NG * NTG, 1) k_fused_tma(const __grid_constant
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const uint32_t *rp = sB + (ty + BY - 1 + r) * BW + tx4;
+                    CVB_BOUNDS(ty + BY - 1 + r >= 0 && (ty + BY - 1 + r) * BW + tx4 + 7 < BW * BH && y0 + ty < H && x0 + tx4 + 3 < W);
                     const uint4 q0 = *reinterpret_cast<const uint4 *>(rp), q1 = *reinterpret_cast<const uint4 *>(rp + 4);
                     const uint32_t w[6] = {q0.y, q0.z, q0.w, q1.x, q1.y, q1.z};      // image x - 1 .. x + 4
 #pragma unroll
@@ -644,6 +647,7 @@ __global__ void __launch_bounds__(NP + NQ, 1) k_fused_pc(const __grid_constant__
                     if (sx < 0 || sx >= AW || sy < 0 || sy >= AH) continue;
                     const uint8_t *s = raw + sy * RAW_PITCH + sx * 3;
                     uint8_t *d = raw + ly * RAW_PITCH + lx * 3;
+                    CVB_BOUNDS(ly >= 0 && ly < AH && lx >= 0 && lx < AW && (d - sRaw) + 2 < (int)S::rawBytes && (s - sRaw) + 2 < (int)S::rawBytes);
                     d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
                 }
                 named_sync<NP>(1);
@@ -655,6 +659,7 @@ __global__ void __launch_bounds__(NP + NQ, 1) k_fused_pc(const __grid_constant__
                 for (int item = tid; item < AH * PAIRS; item += NP) {
                     const int ly = item / PAIRS, lx = 2 * (item - ly * PAIRS);
                     const uint16_t *rp = reinterpret_cast<const uint16_t *>(raw + ly * RAW_PITCH + lx * 3);
+                    CVB_BOUNDS(ly < AH && lx + 1 < AW && (raw - sRaw) + ly * RAW_PITCH + lx * 3 + 5 < (int)S::rawBytes);
                     const uint32_t u0 = rp[0], u1 = rp[1], u2 = rp[2];
                     const Axis2 cy = sAx[AW + ly], c0 = sAx[lx], c1 = sAx[lx + 1];
                     const uint32_t q0 = light_px(sTab, lut, c0, cy, u0 & 0xff, u0 >> 8, u1 & 0xff);
@@ -836,6 +841,8 @@ int launch_pc(cvb_handle *h, const uint8_t *lab, Fused2Args &a)
 }
 
 }  // namespace
+
+CVB_BOUNDS_TU(fused2)
 
 bool fused_tma_applicable(int H, int W, const uint8_t *lab, const uint8_t *out)
 {

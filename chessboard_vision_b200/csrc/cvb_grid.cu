@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(256, CVB_SQ_MINB) k_squares(const SquareArgs a
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int i = i0 + 256 * j;
+                    CVB_BOUNDS(i >= n || (rc.y + div_magic(i, inv_w) < a.BH && rc.x + (i - div_magic(i, inv_w) * w) < a.BW));
                     if (i < n) s_g[i] = (uint8_t)gray_px(c0[j], c1[j], c2[j]);
                 }
             }
@@ -489,3 +490,5 @@ int launch_state_reset(cvb_handle *h, cvb_state *s, int stream)
     CVB_CHECK_CUDA(cudaMemsetAsync(p, 0, n, h->stream));
     return CVB_OK;
 }
+
+CVB_BOUNDS_TU(grid)

@@ -406,3 +406,5 @@ int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_strid
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
+
+CVB_BOUNDS_TU(hough)

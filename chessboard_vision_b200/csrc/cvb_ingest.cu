@@ -141,3 +141,5 @@ int launch_yuv_to_bgr(cvb_handle *h, const uint8_t *src, int format, int n, int 
     LAUNCH_CHECK(h);
     return CVB_OK;
 }
+
+CVB_BOUNDS_TU(ingest)

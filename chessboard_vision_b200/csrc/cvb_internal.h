@@ -77,7 +77,6 @@ struct cvb_handle {
     CvbTables *d_tables = nullptr;
     // bilateral colour LUT cache (device) keyed by sigma_color
     float *d_color = nullptr;
-    cudaTextureObject_t wtex = 0;      // the folded weight table as a 1-D texture (experiments with texture-unit lookups)
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
     DevBuf ws_lab, ws_prof, ws_in, ws_raw, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
@@ -159,6 +158,11 @@ int launch_finish(cvb_handle *h, const uint8_t *src, int n, int H, int W, const 
                   uint8_t *enhanced, uint8_t *gray, uint8_t *blurred, int32_t *hist);
 int launch_otsu(cvb_handle *h, const int32_t *hist, int n, long npx, int32_t *otsu_t);
 int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const int32_t *otsu_t, uint8_t *dst);
+
+// per-translation-unit counters of the debug build's index checks (cvb_device.cuh)
+void cvb_bounds_enhance(unsigned long long *, int *); void cvb_bounds_fused2(unsigned long long *, int *);
+void cvb_bounds_grid(unsigned long long *, int *); void cvb_bounds_canny(unsigned long long *, int *);
+void cvb_bounds_hough(unsigned long long *, int *); void cvb_bounds_ingest(unsigned long long *, int *);
 
 // ---- cvb_ingest.cu ------------------------------------------------------------------------
 size_t cvb_host_frame_bytes(int format, int H, int W);

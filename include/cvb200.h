@@ -353,6 +353,12 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
                  cvb_state *state, int stream0,
                  int32_t *otsu_t, cvb_square_stats *stats);
 
+/* Debug build only (`make -C chessboard_vision_b200/csrc debug` -> libcvb200_dbg.so): number of shared-memory / global
+ * index checks that failed since the library was loaded and the source line of the first one; -1 in the release
+ * library, which carries no checks.  Stands in for compute-sanitizer, which is closed on the target pool; the
+ * reference has no counterpart (its arrays are bounds-checked by NumPy, e.g. grid_extractor.py:46). */
+long long cvb_debug_bounds_violations(cvb_handle *h, int *first_line);
+
 /* ---- camera ingest ---------------------------------------------- */
 /* play_lichess.py:16-18,45 / game_session.py:99,113 receive BGR frames from
  * cv2.VideoCapture.read(), i.e. after OpenCV has converted the camera's native YUV on the

@@ -1,11 +1,13 @@
-"""Small whole-path run for compute-sanitizer (memcheck / racecheck): odd sizes, partial tiles, all op masks."""
+"""Small whole-path run for compute-sanitizer (memcheck / racecheck) and for the debug build's index checks
+(CVB200_LIB=chessboard_vision_b200/libcvb200_dbg.so): odd sizes, partial tiles, all op masks, both ingest formats.
+Prints `bounds violations: N` (-1: release library, no checks compiled in)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from chessboard_vision_b200 import synth
 from chessboard_vision_b200.engine import (Engine, grid_rects, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE)
 eng = Engine(0)
-for (H, W) in ((135, 241), (64, 64), (270, 480)):
+for (H, W) in ((135, 241), (64, 64), (270, 480), (92, 160), (360, 640)):
     f = synth.frame_batch(2, H, W, "board", 1)
     eng.enhance(f)
     eng.bilateral(f[0]); eng.sharpen(f[0]); eng.correct_lighting(f[0]); eng.normalize(f[0])
@@ -18,4 +20,10 @@ for (H, W) in ((135, 241), (64, 64), (270, 480)):
         pp = eng.pipeline_params(squares=eng.square_params(ops=ops, cd_blur=5 if ops != SQ_CD_DETECT else 13), board_size=S)
         eng.pipeline(f, M, rects, pp, st)
     st.free()
+    if W % 2 == 0 and H % 2 == 0:
+        for fmt in ("yuy2", "nv12"):
+            eng.cvt_to_bgr(np.stack([synth.bgr_to_yuv(x, fmt) for x in f]), fmt)
+import ctypes
+line = ctypes.c_int(0)
+print("bounds violations:", eng.lib.cvb_debug_bounds_violations(eng.h, ctypes.byref(line)), "first at line", line.value)
 print("sanitize run done")
