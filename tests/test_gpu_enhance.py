@@ -221,3 +221,25 @@ def test_enhance_4k_vs_oracle_and_stream_state(engine, oracle):
         assert (r["sum"], r["sumsq"], r["sad"], r["has_ref"]) == (o["sum"], o["sumsq"], o["sad"], 1)
         assert r["cd_valid"] == 1 and r["cd_changed"] == cnt and r["cd_zmax"] == np.float32(zmax)
     st.free()
+
+
+def test_two_devices(engine):
+    """Engines on two GPUs in one process: every entry point runs on its handle's own device whatever device the thread
+    had current (only cvb_create / cvb_malloc used to select the device)."""
+    from chessboard_vision_b200 import _lib
+    from chessboard_vision_b200.engine import Engine
+    if _lib.load().cvb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import oracle as O
+    other = Engine(1)                      # leaves device 1 current in this thread
+    try:
+        f = synth.board_frame(135, 240, 3)
+        ref = O.process_pipeline(f, True)
+        assert np.array_equal(engine.process_pipeline(f), ref)        # handle of device 0, first call after Engine(1)
+        assert np.array_equal(other.process_pipeline(f), ref)
+        st0, st1 = engine.new_state(1, 64, 64), other.new_state(1, 64, 64)
+        a = engine.enhance(f); b = other.enhance(f)
+        assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3]
+        st0.free(); st1.free()
+    finally:
+        other.close()
