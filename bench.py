@@ -205,8 +205,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--kind", default="board", choices=["board", "noise"])
-    ap.add_argument("--config", default="throughput", choices=["throughput", "latency", "change64", "streams4k"],
-                    help="throughput = BASELINE.json configs[3] (the metric; default); latency = configs[1]; change64 = configs[2]; "
+    ap.add_argument("--config", default="throughput", choices=["throughput", "enhance480", "latency", "change64", "streams4k"],
+                    help="throughput = BASELINE.json configs[3] (the metric; default); enhance480 = configs[0]; latency = configs[1]; change64 = configs[2]; "
                          "streams4k = configs[4] (tools/bench_modes.py)")
     ap.add_argument("--ingest", default="bgr", choices=["bgr", "yuy2", "nv12"],
                     help="format the frames arrive in: BGR as cv2.VideoCapture.read() returns them (BASELINE configs), or the "
@@ -445,7 +445,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_modes
         side = argparse.Namespace(**vars(args)); side.steps, side.warmup, side.kind = 10, 3, "board"
-        for name in ("latency", "change64", "streams4k"):
+        for name in ("enhance480", "latency", "change64", "streams4k"):
             r = bench_modes.MODES[name]({"eng": eng, "synth": synth, "args": side, "rank": 0, "world": 1, "timed": timed})
             extras["config_" + name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "cpu_baseline",
                                                           "stages_us") if k in r}
@@ -535,6 +535,7 @@ def main():
         tot_ms = sum(v[0] for v in prof.values()) or 1.0
         # algorithmic bytes per frame per kernel
         alg = {"k_tile_hist": 6 * npx, "k_fused": 6 * npx, "k_finish": 8 * npx, "k_threshold": 2 * npx,
+               "k_yuv2bgr": int({"yuy2": 5, "nv12": 4.5}.get(args.ingest, 0) * npx),
                "k_warp": 1012 * 916 * 3 + S * S * 3, "k_squares": S * S * 3 + 64 * 77 * 77 * (1 + 4 + 4 + 4 + 4 + 1),
                "k_clahe_lut": 64 * 256 * 5, "k_otsu": 1024}
         stages = {}
@@ -548,6 +549,10 @@ def main():
         per_frame = traffic.get("dram_bytes_per_frame", {})
         for name in stages:
             stages[name]["traffic_bytes_per_launch"] = per_frame[name] * n if name in per_frame else None
+            pp_ = traffic.get("pipes_pct", {}).get(name)
+            if pp_:           # the pipe ncu shows busiest for this kernel and its utilisation (percent of peak)
+                k_, v_ = max(pp_.items(), key=lambda kv: kv[1])
+                stages[name]["busiest_pipe"] = {"name": k_, "pct": v_}
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
         d = stages[dom]
         pipes = traffic.get("pipes_pct", {}).get(dom, {})
