@@ -47,6 +47,7 @@ def enhance480(ctx):
     try:
         import cv2
         from oracle import ref_cv2
+        nthreads = cv2.getNumThreads()
         ref_cv2.prepare_analysis(ref_cv2.process_pipeline(frames[0]))
         ts = []
         for i in range(10):
@@ -55,8 +56,8 @@ def enhance480(ctx):
         t1 = []
         for i in range(5):
             t0 = time.perf_counter(); ref_cv2.prepare_analysis(ref_cv2.process_pipeline(frames[i % 4])); t1.append((time.perf_counter() - t0) * 1e3)
-        cv2.setNumThreads(0)
-        cpu = {"value": float(np.median(ts)), "unit": "ms/frame", "cores": cv2.getNumThreads(), "kind": "port",
+        cv2.setNumThreads(nthreads)
+        cpu = {"value": float(np.median(ts)), "unit": "ms/frame", "cores": nthreads, "kind": "port",
                "one_thread_ms": float(np.median(t1)),
                "sample": "10 frames with OpenCV's thread pool, 5 frames with one thread",
                "what": "oracle/ref_cv2.py: process_pipeline + prepare_analysis (frame_enhancer.py:148-181) on cv2 %s" % cv2.__version__}
@@ -155,7 +156,8 @@ def change64(ctx):
     try:
         import cv2
         from oracle import ref_cv2
-        cv2.setNumThreads(0)
+        nthreads = cv2.getNumThreads()
+        cv2.setNumThreads(1)
         wb = [ref_cv2.warp_image(f, pts)[0] for f in (prev[0], cur[0])]
         sq = [ref_cv2.split_board(w) for w in wb]
         state = {p: (ref_cv2.preprocess_square(s, 5).astype(np.float32), np.full(s.shape[:2], 100, np.float32)) for p, s in sq[0].items()}
@@ -167,6 +169,7 @@ def change64(ctx):
                 ref_cv2.cd_detect(g, *state[p]); ref_cv2.cd_update(g, *state[p])
                 float(np.mean(cv2.absdiff(g, ref[p])))
         per_pair = (time.perf_counter() - t0) / reps
+        cv2.setNumThreads(nthreads)
         cpu = {"value": 1.0 / per_pair, "unit": "pairs/s", "cores": 1, "kind": "port",
                "sample": "%d pairs of 64 squares on one core" % reps,
                "what": "the cv2 / numpy calls of ChangeDetector._preprocess + detect_changes_detailed (numeric part) + "
