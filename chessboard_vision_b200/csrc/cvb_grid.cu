@@ -6,6 +6,8 @@
 // 124-207,305 (statistics).  Compiled with -fmad=false.
 #include "cvb_device.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 
 static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the ABI");
 
@@ -205,6 +207,16 @@ CVB_DEV int blur_at(const uint16_t *s_h, const int *q, int k_rt, int x, int y, i
     return (int)((s + 32768u) >> 16);
 }
 
+// |g - m| / sqrt(v) in IEEE f32 (change_detector.py:128-129).  A zero numerator is common (a static square whose mean has
+// converged) and sends div.rn's special-operand path through a ~30-instruction subroutine for the whole warp: its
+// quotient is known without dividing (+0 for v > 0 incl. +inf, NaN for v <= 0, -0 or NaN: 0 / sqrt(v) in every case).
+CVB_DEV float cd_zscore(float gf, float m, float v)
+{
+    const float d = fabsf(__fsub_rn(gf, m));
+    if (d == 0.0f) return v > 0.0f ? 0.0f : __int_as_float(0x7fc00000);
+    return __fdiv_rn(d, __fsqrt_rn(v));
+}
+
 template <int OPS>
 // measured on B200 (77-px squares): pixels per thread and round / resident CTAs per SM 4/4: 4.66, 2/6: 4.38, 3/5: 4.60,
 // 1/8: 4.55, 4/3: 5.83 us per frame -- occupancy beats batch depth here
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(256, CVB_SQ_MINB) k_squares(const SquareArgs a
             const float gf = (float)gv[j];
             if (calib) { cd_mean[o] = m[j]; cd_var[o] = v[j]; flags[o] |= 6; }
             if (ops & CVB_SQ_CD_DETECT) {
-                const float z = __fdiv_rn(fabsf(__fsub_rn(gf, m[j])), __fsqrt_rn(v[j]));
+                const float z = cd_zscore(gf, m[j], v[j]);
                 if (z > zthr) ++cd_cnt;
                 if (z != z) cd_nan = true; else cd_zmax = fmaxf(cd_zmax, z);
             }
@@ -438,6 +450,242 @@ __global__ void __launch_bounds__(256, CVB_SQ_MINB) k_squares(const SquareArgs a
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same per-square work for the case every live caller uses (3-channel boards, both blurs 5 x 5, board pitch a
+// multiple of 4 pixels), four pixels per thread.  Groups of 4 pixels are aligned to the BOARD's x grid (x % 4 == 0), not
+// to the square: a group of BGR pixels is then three aligned words, the state planes move as one word (references,
+// gray squares, flags) or one float4 (mean, variance) per group, and the statistics become byte-wise dot products
+// (sum = dp4a(g, 1), sum of squares = dp4a(g, g), SAD = vsadu4, masked region sums = dp4a(g, mask bit)).  Pixels of a
+// group that lie outside the square (its first / last group when the square does not start on the grid) are masked
+// out of every sum and never stored.  Gaussian 5 x 5 as in k_finish: rows by dp4a on packed bytes, columns on packed
+// 16-bit lanes, (sum + 128) >> 8 -- the Q8 x Q8 form of smooth.dispatch.cpp with q = 16 [1 4 6 4 1] reduces to it exactly.
+// REFLECT_101 inside the square: two mirrored rows above / below are staged from their source rows, two mirrored
+// columns left / right are copied in shared memory after the gray pass.
+// ---------------------------------------------------------------------------------------
+template <int OPS>
+#ifndef CVB_SQ4_MINB
+#define CVB_SQ4_MINB 6
+#endif
+__global__ void __launch_bounds__(256, CVB_SQ4_MINB) k_squares4(const SquareArgs a)
+{
+    extern __shared__ __align__(16) uint8_t sq_smem[];
+    __shared__ unsigned long long s_acc[16];
+    __shared__ unsigned s_cd_nan;
+    __shared__ int s_cd_zbits;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sq = blockIdx.x, frame = blockIdx.y;
+    const cvb_rect rc = a.rects[sq];
+    const int w = rc.w, h = rc.h, n = w * h;
+    const int X0 = rc.x & ~3, X1 = (rc.x + w + 3) & ~3, span = X1 - X0, G = span >> 2;
+    const int R = h + 4;                                   // staged rows: local y = -2 .. h + 1
+    const int pitchG = span + 8;                           // gray bytes per staged row: board x = X0 - 4 .. X1 + 3
+    uint8_t *s_g = sq_smem;
+    uint16_t *s_h = reinterpret_cast<uint16_t *>(sq_smem + (((size_t)R * pitchG + 15) & ~(size_t)15));   // [R][span]
+    const size_t plane = (size_t)a.BH * a.BW;
+    const size_t so = (size_t)(a.stream0 + frame) * plane;
+    const uint8_t *board = a.boards + (size_t)frame * plane * 3;
+    const bool selected = a.select ? a.select[sq] != 0 : true;
+    constexpr int ops = OPS;
+
+    if (tid < 16) s_acc[tid] = 0ull;
+    if (tid == 0) { s_cd_nan = 0; s_cd_zbits = __float_as_int(-INFINITY); }
+    const unsigned inv_g = magic_of(G);
+    // ---- 1: gray of the staged rows, whole aligned groups (neighbouring squares' pixels inside a group are harmless) ----
+    for (int i = tid; i < R * G; i += 256) {
+        const int r = div_magic(i, inv_g), g = i - r * G;
+        const int ys = rc.y + reflect_near(r - 2, h);
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(board + ((size_t)ys * a.BW + X0 + 4 * g) * 3);
+        CVB_BOUNDS(ys >= 0 && ys < a.BH && X0 + 4 * g + 3 < a.BW && r * pitchG + 4 + 4 * g + 3 < R * pitchG);
+        const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+        *reinterpret_cast<uint32_t *>(s_g + r * pitchG + 4 + 4 * g) = gray4_from_words(w0, w1, w2);
+    }
+    __syncthreads();
+    // ---- mirrored columns (local x = -1, -2, w, w + 1) ----
+    {
+        const int cl = rc.x - X0 + 4, cr = cl + w - 1;
+        for (int r = tid; r < R; r += 256) {
+            uint8_t *row = s_g + r * pitchG;
+            const uint8_t l1 = row[cl + 1], l2 = row[cl + 2], r1 = row[cr - 1], r2 = row[cr - 2];
+            row[cl - 1] = l1; row[cl - 2] = l2; row[cr + 1] = r1; row[cr + 2] = r2;
+        }
+    }
+    __syncthreads();
+    // ---- 2: horizontal [1 4 6 4 1], four outputs per item ----
+    for (int i = tid; i < R * G; i += 256) {
+        const int r = div_magic(i, inv_g), g = i - r * G;
+        const uint32_t *gp = reinterpret_cast<const uint32_t *>(s_g + r * pitchG + 4 * g);
+        const uint32_t wa = gp[0], wb = gp[1], wc = gp[2];          // board x = X0 + 4g - 4 .. X0 + 4g + 7
+        constexpr uint32_t kW = 1u | (4u << 8) | (6u << 16) | (4u << 24);
+        const uint32_t h0 = __dp4a(__byte_perm(wa, wb, 0x5432), kW, (wb >> 16) & 0xffu);
+        const uint32_t h1 = __dp4a(__byte_perm(wa, wb, 0x6543), kW, wb >> 24);
+        const uint32_t h2 = __dp4a(wb, kW, wc & 0xffu);
+        const uint32_t h3 = __dp4a(__byte_perm(wb, wc, 0x4321), kW, (wc >> 8) & 0xffu);
+        *reinterpret_cast<uint2 *>(s_h + r * span + 4 * g) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    }
+    __syncthreads();
+
+    const size_t first = so + (size_t)rc.y * a.BW + rc.x;
+    const bool state = a.flags != nullptr;
+    const int fl0 = state ? a.flags[first] : 0;
+    const bool has_ref = (fl0 & 1) != 0;
+    const bool has_cd = (fl0 & 6) == 6;
+    const bool need_pd = (ops & (CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF)) != 0;
+    const bool need_cd = (ops & (CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE)) != 0 && selected && state;
+    const bool calib = (ops & CVB_SQ_CD_CALIBRATE) != 0;
+    const bool cd_live = need_cd && (calib || has_cd);
+    const float zthr = a.p.z_threshold, alpha = a.p.alpha, oma = a.p.one_minus_alpha, minvar = a.p.min_variance,
+                initvar = a.p.initial_variance;
+    unsigned sum = 0, sad = 0, rsum[6] = {0, 0, 0, 0, 0, 0}, rcnt[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long sumsq = 0;
+    unsigned cd_cnt = 0;
+    float cd_zmax = -INFINITY;
+    bool cd_nan = false;
+    const uint8_t *mask = a.masks + a.mask_ofs[sq];
+    // ---- 3: vertical pass, statistics, state ----
+    for (int i = tid; i < h * G; i += 256) {
+        const int y = div_magic(i, inv_g), g = i - y * G;
+        const uint16_t *hrow = s_h + y * span + 4 * g;              // staged row y is local y - 2
+        const uint2 r0 = *reinterpret_cast<const uint2 *>(hrow), r1 = *reinterpret_cast<const uint2 *>(hrow + span),
+                    r2 = *reinterpret_cast<const uint2 *>(hrow + 2 * span), r3 = *reinterpret_cast<const uint2 *>(hrow + 3 * span),
+                    r4 = *reinterpret_cast<const uint2 *>(hrow + 4 * span);
+        const uint32_t lo = r0.x + 4 * r1.x + 6 * r2.x + 4 * r3.x + r4.x, hi = r0.y + 4 * r1.y + 6 * r2.y + 4 * r3.y + r4.y;
+        const uint32_t o0 = ((lo & 0xffff) + 128) >> 8, o1 = ((lo >> 16) + 128) >> 8, o2 = ((hi & 0xffff) + 128) >> 8,
+                       o3 = ((hi >> 16) + 128) >> 8;
+        const int X = X0 + 4 * g, xl = X - rc.x;                    // local x of the group's first pixel (may be -3 .. -1)
+        uint32_t vbytes = 0;                                        // 0xff in the byte lanes of pixels inside the square
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (xl + j >= 0 && xl + j < w) vbytes |= 0xffu << (8 * j);
+        if (!vbytes) continue;
+        const bool full = vbytes == 0xffffffffu;
+        const uint32_t gw = (o0 | (o1 << 8) | (o2 << 16) | (o3 << 24)) & vbytes;
+        const unsigned ofs = (unsigned)((rc.y + y) * a.BW + X);      // offset inside a state plane (multiple of 4)
+        CVB_BOUNDS(rc.y + y < a.BH && X + 3 < a.BW && (ofs & 3u) == 0u);
+        if (ops & CVB_SQ_PD_STATS) {
+            uint32_t mw = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (vbytes & (0xffu << (8 * j))) mw |= (uint32_t)mask[y * w + xl + j] << (8 * j);
+            sum += __dp4a(gw, 0x01010101u, 0u);
+            sumsq += __dp4a(gw, gw, 0u);
+            if (has_ref) sad += __vsadu4(gw, *reinterpret_cast<const uint32_t *>(a.pd_ref + so + ofs) & vbytes);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t sel = (mw >> k) & 0x01010101u;
+                rsum[k] += __dp4a(gw, sel, 0u);
+                rcnt[k] += __popc(sel);
+            }
+        }
+        if (state && need_pd) {
+            uint8_t *pc = a.pd_cur + so + ofs;
+            const bool setref = (ops & CVB_SQ_PD_SET_REF) && selected;
+            if (full) {
+                *reinterpret_cast<uint32_t *>(pc) = gw;
+                if (setref) {
+                    *reinterpret_cast<uint32_t *>(a.pd_ref + so + ofs) = gw;
+                    uint32_t *fp = reinterpret_cast<uint32_t *>(a.flags + so + ofs);
+                    *fp = *fp | 0x01010101u;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (vbytes & (0xffu << (8 * j))) {
+                        const uint8_t v = (uint8_t)(gw >> (8 * j));
+                        pc[j] = v;
+                        if (setref) { a.pd_ref[so + ofs + j] = v; a.flags[so + ofs + j] |= 1; }
+                    }
+            }
+        }
+        if (cd_live) {
+            float *pm = a.cd_mean + so + ofs, *pv = a.cd_var + so + ofs;
+            float m[4], v[4];
+            if (calib) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { m[j] = (float)((gw >> (8 * j)) & 0xffu); v[j] = initvar; }
+            } else if (full) {
+                const float4 m4 = *reinterpret_cast<const float4 *>(pm), v4 = *reinterpret_cast<const float4 *>(pv);
+                m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w; v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    m[j] = 0.f; v[j] = 1.f;
+                    if (vbytes & (0xffu << (8 * j))) { m[j] = pm[j]; v[j] = pv[j]; }
+                }
+            }
+            float nm[4], nv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                nm[j] = m[j]; nv[j] = v[j];
+                if (!(vbytes & (0xffu << (8 * j)))) continue;
+                const float gf = (float)((gw >> (8 * j)) & 0xffu);
+                if (ops & CVB_SQ_CD_DETECT) {
+                    const float z = cd_zscore(gf, m[j], v[j]);
+                    if (z > zthr) ++cd_cnt;
+                    if (z != z) cd_nan = true; else cd_zmax = fmaxf(cd_zmax, z);
+                }
+                if (ops & CVB_SQ_CD_UPDATE) {
+                    // change_detector.py:82-89, every product and sum rounded on its own
+                    nm[j] = __fadd_rn(__fmul_rn(oma, m[j]), __fmul_rn(alpha, gf));
+                    const float d = __fsub_rn(gf, nm[j]);
+                    float t = __fadd_rn(__fmul_rn(oma, v[j]), __fmul_rn(alpha, __fmul_rn(d, d)));
+                    if (!(t > minvar) && t == t) t = minvar;       // np.maximum keeps NaN
+                    nv[j] = t;
+                }
+            }
+            if (calib || (ops & CVB_SQ_CD_UPDATE)) {
+                if (full) {
+                    *reinterpret_cast<float4 *>(pm) = make_float4(nm[0], nm[1], nm[2], nm[3]);
+                    *reinterpret_cast<float4 *>(pv) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+                    if (calib) {
+                        uint32_t *fp = reinterpret_cast<uint32_t *>(a.flags + so + ofs);
+                        *fp = *fp | 0x06060606u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (vbytes & (0xffu << (8 * j))) {
+                            pm[j] = nm[j]; pv[j] = nv[j];
+                            if (calib) a.flags[so + ofs + j] |= 6;
+                        }
+                }
+            }
+        }
+    }
+    if (!a.stats) return;
+
+    // ---- block reduction (same record as k_squares) ----
+    unsigned long long vals[16] = {sum, sumsq, sad, rsum[0], rcnt[0], rsum[1], rcnt[1], rsum[2], rsum[3], rsum[4], rsum[5],
+                                   rcnt[2], rcnt[3], rcnt[4], rcnt[5], cd_cnt};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned long long r = warp_sum_ull(vals[k]);
+        if (lane == 0 && r) atomicAdd(&s_acc[k], r);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cd_zmax = fmaxf(cd_zmax, __shfl_xor_sync(0xffffffffu, cd_zmax, o));
+    const unsigned any_nan = __ballot_sync(0xffffffffu, cd_nan);
+    if (lane == 0) {
+        atomicMax(&s_cd_zbits, __float_as_int(cd_zmax));
+        if (any_nan) atomicOr(&s_cd_nan, 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cvb_square_stats st;
+        memset(&st, 0, sizeof st);
+        st.n = n;
+        st.has_ref = has_ref ? 1 : 0;
+        st.sum = (uint32_t)s_acc[0]; st.sumsq = s_acc[1]; st.sad = (uint32_t)s_acc[2];
+        st.center_sum = (uint32_t)s_acc[3]; st.center_cnt = (uint32_t)s_acc[4];
+        st.border_sum = (uint32_t)s_acc[5]; st.border_cnt = (uint32_t)s_acc[6];
+        for (int k = 0; k < 4; ++k) { st.ring_sum[k] = (uint32_t)s_acc[7 + k]; st.ring_cnt[k] = (uint32_t)s_acc[11 + k]; }
+        const bool cd_ran = need_cd && (ops & CVB_SQ_CD_DETECT) && (has_cd || calib);
+        st.cd_valid = cd_ran ? 1 : 0;
+        st.cd_changed = (int32_t)s_acc[15];
+        st.cd_zmax = s_cd_nan ? __int_as_float(0x7fc00000) : __int_as_float(s_cd_zbits);
+        a.stats[(size_t)frame * gridDim.x + sq] = st;
+    }
+}
+
 int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, int C, const cvb_rect *d_rects,
                    const int32_t *d_mask_ofs, const uint8_t *d_masks, int n_sq, int max_px, const uint8_t *d_select,
                    cvb_state *st, int stream0, const cvb_square_params &p, const int *pd_q, const int *cd_q,
@@ -456,6 +704,49 @@ int launch_squares(cvb_handle *h, const uint8_t *boards, int n, int BH, int BW, 
         return CVB_ERR_INVALID;
     }
     dim3 grid(n_sq, n);
+    // four-pixels-per-thread form: 3-channel boards, both blurs 5 x 5, board rows and planes that keep 4-pixel groups
+    // aligned, squares of at least 3 x 3 pixels (single-bounce mirrors), one of the op masks the callers use
+    {
+        bool fast = C == 3 && p.pd_blur == 5 && p.cd_blur == 5 && BW % 4 == 0 && ((size_t)BH * BW) % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(boards) & 3) == 0 && !getenv("CVB_SQUARES_OLD");
+        int max_w = 0, max_h = 0;
+        for (const cvb_rect &r : h->rect_cache.rects) {
+            fast = fast && r.w >= 3 && r.h >= 3;
+            max_w = std::max(max_w, r.w); max_h = std::max(max_h, r.h);
+        }
+        fast = fast && (int)h->rect_cache.rects.size() == n_sq;
+        void (*k4)(const SquareArgs) = nullptr;
+        switch (p.ops) {
+        case CVB_SQ_PD_STATS: k4 = k_squares4<CVB_SQ_PD_STATS>; break;
+        case CVB_SQ_PD_SET_REF: k4 = k_squares4<CVB_SQ_PD_SET_REF>; break;
+        case CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF: k4 = k_squares4<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF>; break;
+        case CVB_SQ_CD_CALIBRATE: k4 = k_squares4<CVB_SQ_CD_CALIBRATE>; break;
+        case CVB_SQ_CD_DETECT: k4 = k_squares4<CVB_SQ_CD_DETECT>; break;
+        case CVB_SQ_CD_UPDATE: k4 = k_squares4<CVB_SQ_CD_UPDATE>; break;
+        case CVB_SQ_PD_STATS | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE:
+            k4 = k_squares4<CVB_SQ_PD_STATS | CVB_SQ_CD_DETECT | CVB_SQ_CD_UPDATE>; break;
+        case CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE:
+            k4 = k_squares4<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE>; break;
+        case CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT:
+            k4 = k_squares4<CVB_SQ_PD_STATS | CVB_SQ_PD_SET_REF | CVB_SQ_CD_CALIBRATE | CVB_SQ_CD_DETECT>; break;
+        default: break;
+        }
+        if (fast && k4) {
+            const int span = max_w + 6, rows = max_h + 4;
+            const size_t smem4 = (((size_t)rows * (span + 8) + 15) & ~(size_t)15) + (size_t)rows * span * 2;
+            if (smem4 <= 200 * 1024) {
+                size_t &cur4 = h->squares_smem_attr[(const void *)k4];
+                if (smem4 > 48 * 1024 && smem4 > cur4) {
+                    CVB_CHECK_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                    cur4 = smem4;
+                }
+                PROF(h, "k_squares");
+                k4<<<grid, 256, smem4, h->stream>>>(a);
+                LAUNCH_CHECK(h);
+                return CVB_OK;
+            }
+        }
+    }
     // the common op masks get a specialised instance (flag tests folded at compile time)
     void (*kern)(const SquareArgs) = k_squares<-1>;
     switch (p.ops) {

@@ -181,3 +181,50 @@ def test_full_pipeline_matches_composition(engine, oracle):
             _check_pd(stats[i, j], o[j][1], False)
             assert stats[i, j]["cd_valid"] == 1 and stats[i, j]["cd_changed"] == 0
     st.free()
+
+
+@pytest.mark.parametrize("grid", ["linear", "smart", "odd"])
+def test_cd_special_values_and_partial_groups(engine, oracle, grid):
+    """The 4-pixels-per-thread square kernel on squares that do not start on its 4-pixel grid, with state planes
+    holding the values its shortcuts must respect: mean == gray (zero numerator) over variances 0, -0, negative,
+    NaN, +inf, denormal and ordinary, and NaN / inf means.  Counts, z-max (NaN propagates as in np.max) and the
+    updated planes equal the oracle bit for bit; pixels of neighbouring squares stay untouched."""
+    S = 620 if grid != "odd" else 124
+    board = synth.board_frame(S, S, 21)
+    if grid == "linear":
+        rects, _ = grid_rects(S)
+    elif grid == "smart":
+        rects, _ = grid_rects(S, synth.CALIB_GRID_X, synth.CALIB_GRID_Y)
+    else:
+        rects = [(1, 2, 13, 9), (17, 3, 5, 3), (23, 1, 3, 17), (30, 30, 41, 37), (75, 5, 46, 50), (2, 60, 7, 60)]
+    st = engine.new_state(1, S, S)
+    engine.squares(board, rects, engine.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE), st)
+    mean, var = st.get(0, _lib.PLANE_CD_MEAN), st.get(0, _lib.PLANE_CD_VAR)
+    specials = np.array([0.0, -0.0, -3.0, np.nan, np.inf, 1e-40, 7.5, 100.0], np.float32)
+    rng = np.random.default_rng(5)
+    var[...] = specials[rng.integers(0, len(specials), var.shape)]
+    weird = rng.random(mean.shape) < 0.02
+    mean[weird] = np.array([np.nan, np.inf, -np.inf], np.float32)[rng.integers(0, 3, int(weird.sum()))]
+    st.set(0, _lib.PLANE_CD_MEAN, mean); st.set(0, _lib.PLANE_CD_VAR, var)
+    before_cur = st.get(0, _lib.PLANE_PD_CUR)
+    stats = engine.squares(board, rects, engine.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE), st)
+    m2, v2 = st.get(0, _lib.PLANE_CD_MEAN), st.get(0, _lib.PLANE_CD_VAR)
+    inside = np.zeros((S, S), bool)
+    for j, (x, y, w, h) in enumerate(rects):
+        g = oracle.square_preprocess(board[y:y + h, x:x + w], 5)
+        m, v = np.ascontiguousarray(mean[y:y + h, x:x + w]), np.ascontiguousarray(var[y:y + h, x:x + w])
+        cnt, zmax = oracle.cd_detect(g, m, v, 2.5)
+        assert int(stats[0, j]["cd_changed"]) == cnt, (grid, j)
+        assert np.float32(stats[0, j]["cd_zmax"]).tobytes() == np.float32(zmax).tobytes() or (np.isnan(zmax) and np.isnan(stats[0, j]["cd_zmax"]))
+        oracle.cd_update(g, m, v, 0.1)          # in place
+        # bit-equal, except that a NaN may carry another payload (x86 keeps the operand's, the GPU returns the canonical one)
+        same = lambda a, b: np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(b)]) and \
+            np.array_equal(np.isnan(a), np.isnan(b))
+        assert same(m, np.ascontiguousarray(m2[y:y + h, x:x + w])), (grid, j)
+        assert same(v, np.ascontiguousarray(v2[y:y + h, x:x + w])), (grid, j)
+        assert np.array_equal(st.get(0, _lib.PLANE_PD_CUR)[y:y + h, x:x + w], g)
+        inside[y:y + h, x:x + w] = True
+    # nothing outside the squares was written
+    assert m2[~inside].tobytes() == mean[~inside].tobytes() and v2[~inside].tobytes() == var[~inside].tobytes()
+    assert np.array_equal(st.get(0, _lib.PLANE_PD_CUR)[~inside], before_cur[~inside])
+    st.free()
