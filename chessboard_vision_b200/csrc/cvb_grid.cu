@@ -17,72 +17,81 @@ static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the 
 // WarpPerspectiveInvoker + remapBilinear): destination -> source coordinates in
 // f64 with the invoker's 64-column block association, fixed point with 5
 // fractional bits, weights (32-ax)(32-ay).., (sum + 512) >> 10.
-// One thread per destination pixel.
 // ---------------------------------------------------------------------------------------
+// One thread per destination column and four destination rows (a CTA covers 64 x 16 pixels): the block set-up and the
+// barrier are shared by four pixels and the twelve source bytes of four independent pixels are in flight together
+// (the kernel was bound by issue slots and load latency: 204 instructions per pixel, 31 % long-scoreboard stalls).
+constexpr int WARP_ROWS = 16;
 __global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, int H, int W,
                                               const double *__restrict__ minv, int n_mats, int OH, int OW, int rot180,
                                               uint8_t *__restrict__ dst)
 {
     // X0, Y0, W0 of a 64-column block row (imgwarp.cpp forms them once per block and adds M * x1 per pixel):
     // computed by one thread per row of the CTA, read back by the 64 threads of that row
-    __shared__ double s_row[4][3];
+    __shared__ double s_row[WARP_ROWS][3];
     __shared__ double s_m[3];
     const int frame = blockIdx.z;
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), ty = threadIdx.x >> 6, y = blockIdx.y * 4 + ty;
-    if (threadIdx.x < 4) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), ty = threadIdx.x >> 6, y0 = blockIdx.y * WARP_ROWS;
+    if (threadIdx.x < WARP_ROWS) {
         const double *M = minv + (n_mats == 1 ? 0 : (size_t)frame * 9);
-        const double bx = (double)(blockIdx.x * 64), yy = (double)(blockIdx.y * 4 + threadIdx.x);
+        const double bx = (double)(blockIdx.x * 64), yy = (double)(y0 + threadIdx.x);
         s_row[threadIdx.x][0] = __dadd_rn(__dadd_rn(__dmul_rn(M[0], bx), __dmul_rn(M[1], yy)), M[2]);
         s_row[threadIdx.x][1] = __dadd_rn(__dadd_rn(__dmul_rn(M[3], bx), __dmul_rn(M[4], yy)), M[5]);
         s_row[threadIdx.x][2] = __dadd_rn(__dadd_rn(__dmul_rn(M[6], bx), __dmul_rn(M[7], yy)), M[8]);
         if (threadIdx.x == 0) { s_m[0] = M[0]; s_m[1] = M[3]; s_m[2] = M[6]; }
     }
     __syncthreads();
-    if (x >= OW || y >= OH) return;
+    if (x >= OW) return;
     const double x1 = (double)(x & 63);
-    double Wd = __dadd_rn(s_row[ty][2], __dmul_rn(s_m[2], x1));
-    Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
-    double fX = __dmul_rn(__dadd_rn(s_row[ty][0], __dmul_rn(s_m[0], x1)), Wd);
-    double fY = __dmul_rn(__dadd_rn(s_row[ty][1], __dmul_rn(s_m[1], x1)), Wd);
-    fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
-    fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
-    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-    const int ax = X & 31, ay = Y & 31;
-    const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+    const double mx0 = __dmul_rn(s_m[0], x1), mx1 = __dmul_rn(s_m[1], x1), mx2 = __dmul_rn(s_m[2], x1);
     const uint8_t *img = src + (size_t)frame * H * W * 3;
-    int acc[3] = {0, 0, 0};
-    if (sx >= 0 && sx + 1 < W && sy >= 0 && sy + 1 < H) {
-        // all four taps inside (almost every pixel): two row pointers, constant byte offsets
-        const uint8_t *p = img + ((size_t)sy * W + sx) * 3, *q = p + (size_t)W * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] = w00 * p[c] + w01 * p[3 + c] + w10 * q[c] + w11 * q[3 + c];
-    } else {
-        const bool x0in = sx >= 0 && sx < W, x1in = sx + 1 >= 0 && sx + 1 < W;
-        const bool y0in = sy >= 0 && sy < H, y1in = sy + 1 >= 0 && sy + 1 < H;
-        if (y0in) {
-            const uint8_t *r = img + (size_t)sy * W * 3;
-            if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
-            if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w01 * p[0]; acc[1] += w01 * p[1]; acc[2] += w01 * p[2]; }
+    for (int k = 0; k < WARP_ROWS / 4; ++k) {
+        const int ly = ty + 4 * k, y = y0 + ly;
+        if (y >= OH) break;
+        double Wd = __dadd_rn(s_row[ly][2], mx2);
+        Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
+        double fX = __dmul_rn(__dadd_rn(s_row[ly][0], mx0), Wd);
+        double fY = __dmul_rn(__dadd_rn(s_row[ly][1], mx1), Wd);
+        fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+        fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+        const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+        const int ax = X & 31, ay = Y & 31;
+        const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;
+        int acc[3] = {0, 0, 0};
+        if (sx >= 0 && sx + 1 < W && sy >= 0 && sy + 1 < H) {
+            // all four taps inside (almost every pixel): two row pointers, constant byte offsets
+            const uint8_t *p = img + ((size_t)sy * W + sx) * 3, *q = p + (size_t)W * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] = w00 * p[c] + w01 * p[3 + c] + w10 * q[c] + w11 * q[3 + c];
+        } else {
+            const bool x0in = sx >= 0 && sx < W, x1in = sx + 1 >= 0 && sx + 1 < W;
+            const bool y0in = sy >= 0 && sy < H, y1in = sy + 1 >= 0 && sy + 1 < H;
+            if (y0in) {
+                const uint8_t *r = img + (size_t)sy * W * 3;
+                if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
+                if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w01 * p[0]; acc[1] += w01 * p[1]; acc[2] += w01 * p[2]; }
+            }
+            if (y1in) {
+                const uint8_t *r = img + (size_t)(sy + 1) * W * 3;
+                if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w10 * p[0]; acc[1] += w10 * p[1]; acc[2] += w10 * p[2]; }
+                if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w11 * p[0]; acc[1] += w11 * p[1]; acc[2] += w11 * p[2]; }
+            }
         }
-        if (y1in) {
-            const uint8_t *r = img + (size_t)(sy + 1) * W * 3;
-            if (x0in) { const uint8_t *p = r + (size_t)sx * 3; acc[0] += w10 * p[0]; acc[1] += w10 * p[1]; acc[2] += w10 * p[2]; }
-            if (x1in) { const uint8_t *p = r + (size_t)(sx + 1) * 3; acc[0] += w11 * p[0]; acc[1] += w11 * p[1]; acc[2] += w11 * p[2]; }
-        }
+        // cv2.rotate(warped, ROTATE_180) (game_session.py:125-126) is a permutation of the destination pixels
+        const int oy = rot180 ? OH - 1 - y : y, ox = rot180 ? OW - 1 - x : x;
+        uint8_t *o = dst + ((size_t)frame * OH * OW + (size_t)oy * OW + ox) * 3;
+        o[0] = (uint8_t)((acc[0] + 512) >> 10);
+        o[1] = (uint8_t)((acc[1] + 512) >> 10);
+        o[2] = (uint8_t)((acc[2] + 512) >> 10);
     }
-    // cv2.rotate(warped, ROTATE_180) (game_session.py:125-126) is a permutation of the destination pixels
-    const int oy = rot180 ? OH - 1 - y : y, ox = rot180 ? OW - 1 - x : x;
-    uint8_t *o = dst + ((size_t)frame * OH * OW + (size_t)oy * OW + ox) * 3;
-    o[0] = (uint8_t)((acc[0] + 512) >> 10);
-    o[1] = (uint8_t)((acc[1] + 512) >> 10);
-    o[2] = (uint8_t)((acc[2] + 512) >> 10);
 }
 
 int launch_warp(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, const double *d_minv, int n_mats, int out_h,
                 int out_w, int rot180, uint8_t *warped)
 {
-    dim3 grid((out_w + 63) / 64, (out_h + 3) / 4, n);
+    dim3 grid((out_w + 63) / 64, (out_h + WARP_ROWS - 1) / WARP_ROWS, n);
     PROF(h, "k_warp");
     k_warp<<<grid, 256, 0, h->stream>>>(bgr, H, W, d_minv, n_mats, out_h, out_w, rot180, warped);
     LAUNCH_CHECK(h);
