@@ -21,6 +21,7 @@ static_assert(sizeof(cvb_square_stats) == 128, "cvb_square_stats is part of the 
 // One thread per destination column and four destination rows (a CTA covers 64 x 16 pixels): the block set-up and the
 // barrier are shared by four pixels and the twelve source bytes of four independent pixels are in flight together
 // (the kernel was bound by issue slots and load latency: 204 instructions per pixel, 31 % long-scoreboard stalls).
+// Loading the source bytes of all four pixels before any arithmetic was measured too: 92 registers, 3.6 us instead of 2.3.
 constexpr int WARP_ROWS = 16;
 __global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, int H, int W,
                                               const double *__restrict__ minv, int n_mats, int OH, int OW, int rot180,
@@ -53,9 +54,12 @@ __global__ void __launch_bounds__(256) k_warp(const uint8_t *__restrict__ src, i
         Wd = Wd != 0.0 ? __ddiv_rn(32.0, Wd) : 0.0;
         double fX = __dmul_rn(__dadd_rn(s_row[ly][0], mx0), Wd);
         double fY = __dmul_rn(__dadd_rn(s_row[ly][1], mx1), Wd);
-        fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
-        fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-        const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+        // imgwarp.cpp clamps fX / fY to [INT_MIN, INT_MAX] with std::min / std::max and rounds (saturate_cast<int>):
+        // cvt.rni.s32.f64 saturates to the same two values, and a NaN -- which std::min((double)INT_MAX, NaN) turns into
+        // INT_MAX -- is the one case it maps elsewhere (to 0).  Same integers, ~25 instructions less than fmin / fmax.
+        int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+        if (fX != fX) X = 2147483647;
+        if (fY != fY) Y = 2147483647;
         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
         const int ax = X & 31, ay = Y & 31;
         const int w00 = (32 - ax) * (32 - ay), w01 = ax * (32 - ay), w10 = (32 - ax) * ay, w11 = ax * ay;

@@ -228,3 +228,22 @@ def test_cd_special_values_and_partial_groups(engine, oracle, grid):
     assert m2[~inside].tobytes() == mean[~inside].tobytes() and v2[~inside].tobytes() == var[~inside].tobytes()
     assert np.array_equal(st.get(0, _lib.PLANE_PD_CUR)[~inside], before_cur[~inside])
     st.free()
+
+
+def test_warp_extreme_coordinates(engine, oracle):
+    """Homographies whose horizon crosses the destination: W passes through 0, source coordinates overflow int32 or
+    become infinite; the saturating conversion of the kernel equals imgwarp.cpp's clamp + cvRound (the oracle)."""
+    img = synth.noise_frame(120, 160, 4)
+    rng = np.random.default_rng(9)
+    mats = []
+    for i in range(12):
+        M = np.eye(3)
+        M[2, 0], M[2, 1] = rng.uniform(-0.05, 0.05, 2)          # W = 0 somewhere inside the 100 x 100 output
+        M[2, 2] = rng.uniform(-1.0, 1.0)
+        M[0, 2], M[1, 2] = rng.uniform(-1e6, 1e6, 2)
+        M[0, 0] *= 10.0 ** rng.integers(0, 9)
+        mats.append(M)
+    mats.append(np.array([[1, 0, 0], [0, 1, 0], [0.01, 0, -0.5]], np.float64))      # exact zero of W at x = 50
+    mats.append(np.array([[1e300, 0, 0], [0, 1e300, 0], [0, 0, 1e-300]], np.float64))  # products overflow to inf
+    for M in mats:
+        assert np.array_equal(engine.warp(img, M, 100), oracle.warp(img, M, 100)), M
