@@ -26,6 +26,7 @@ def main():
     for r in data:
         name = r[idx["Kernel Name"]]
         short = name.replace("<unnamed>::", "").split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+        short = {"k_squares4": "k_squares"}.get(short, short)      # same PROF label in the library (cvb_grid.cu)
         if short in seen:
             continue
         seen.add(short)
