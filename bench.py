@@ -573,10 +573,11 @@ def main():
                                       "what": "whole step against the 19 N bytes per frame an HBM-bound chain would move"},
                     "note": "achieved / frac are the dominant kernel's ALGORITHMIC HBM bytes over its duration, as the contract "
                             "defines them; that kernel (49-tap bilateral + lighting + sharpen) is not HBM-bound: `bound` names "
-                            "the pipe ncu shows busiest, and tools/ubench_taps.cu (profiles/r02_ubench_taps.txt) gives its "
-                            "floor: one bilateral tap costs ~5 clk per warp and SM sub-partition whatever the encoding, "
-                            "~30 us per 1080p frame for the kernel at 100 % pipe efficiency; the per-stage table gives the "
-                            "streaming kernels' HBM fractions", "stages": stages}
+                            "the pipe ncu shows busiest; tools/ubench_taps.cu and tools/ubench_bilateral.cu (profiles/"
+                            "r02_notes.md section 1) time the tap: 10.4 clk per warp and SM sub-partition for its 7 "
+                            "instructions in isolation, 12.5 inside the stage in every exact encoding, i.e. the bilateral "
+                            "stage alone is ~37 us per 1080p frame; the per-stage table gives the streaming kernels' HBM "
+                            "fractions", "stages": stages}
         fp32_ops = 49 * 8 * npx * n       # 49 taps x (vabsdiff, LUT load, mul, add, 3 fma, convert) per pixel, lower bound
         roofline["fp32_pipe"] = {"ops_per_launch_lower_bound": fp32_ops,
                                  "achieved_tops": fp32_ops / (stages["k_fused"]["ms_per_launch"] / 1e3) / 1e12

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(1024, 1) bench(int iters, float* out, long lon
     __syncthreads();
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm) + (threadIdx.x & 31) * 4;
     float f[8]; u64 p[8]; uint32_t u[8];
-    for (int i = 0; i < 8; ++i) { f[i] = 1.0f + threadIdx.x * 1e-6f + i; p[i] = pk(f[i], f[i] + 1); u[i] = threadIdx.x * 2654435761u + i * 40503u; }
+    for (int i = 0; i < 8; ++i) { f[i] = 1.0f + threadIdx.x * 1e-6f + i; p[i] = pk(f[i], f[i] + 1); u[i] = (threadIdx.x * 2654435761u + i * 40503u) & 0x3f3f3f3fu; }   // byte sums <= 252: table index stays inside 64 KB
     const float w = 0.999f + 1e-9f * threadIdx.x; const u64 w2 = pk(w, w + 1e-6f);
     __syncthreads();
     long long t0 = clock64();
@@ -44,31 +44,43 @@ __global__ void __launch_bounds__(1024, 1) bench(int iters, float* out, long lon
                 if (MODE == 7) u[i] = prmt(u[i], 0x7540 + (i & 3));
                 if (MODE == 8) f[i] = lds(sbase + ((__float_as_uint(f[i]) >> 3) & 0x3f80));          // lane-private: conflict-free
                 if (MODE == 9) {   // old tap: SAD, LEA, LDS, FADD, 3 FFMA   (7 instr)
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = lds(lea(s, sbase));
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = lds(lea(s, sbase));
                     f[0] = fadd(f[0], ww); f[1] = ffma(f[5], ww, f[1]); f[2] = ffma(f[6], ww, f[2]); f[3] = ffma(f[7], ww, f[3]);
                 }
                 if (MODE == 10) {  // new tap: SAD, LEA, LDS, FMUL, 2 FFMA2 (6 instr)
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = fmul(lds(lea(s, sbase)), w);
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = fmul(lds(lea(s, sbase)), w);
                     p[0] = fma2(p[4], pk(ww, ww), p[0]); p[1] = fma2(p[5], pk(ww, ww), p[1]);
                 }
                 if (MODE == 11) {  // new tap, folded: SAD, LEA, LDS, 2 FFMA2 (5 instr)
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = lds(lea(s, sbase));
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = lds(lea(s, sbase));
                     p[0] = fma2(p[4], pk(ww, ww), p[0]); p[1] = fma2(p[5], pk(ww, ww), p[1]);
                 }
                 if (MODE == 12) {  // scalar + private table: SAD, LEA, LDS, FMUL, FADD, 3 FFMA (8 instr)
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = fmul(lds(lea(s, sbase)), w);
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = fmul(lds(lea(s, sbase)), w);
                     f[0] = fadd(f[0], ww); f[1] = ffma(f[5], ww, f[1]); f[2] = ffma(f[6], ww, f[2]); f[3] = ffma(f[7], ww, f[3]);
                 }
                 if (MODE == 13) {  // 4 independent pixels, scalar: per tap 4x(SAD LEA LDS FADD 3FFMA) -- more ILP
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = lds(lea(s, sbase));
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = lds(lea(s, sbase));
                     const int j = i & 1;
                     f[4 * j] = fadd(f[4 * j], ww); f[4 * j + 1] = ffma(w, ww, f[4 * j + 1]); f[4 * j + 2] = ffma(w, ww, f[4 * j + 2]); f[4 * j + 3] = ffma(w, ww, f[4 * j + 3]);
                 }
                 if (MODE == 14) {  // 2 independent pixels packed
-                    uint32_t s = sad(u[i], u[(i + 1) & 7]) & 63; float ww = lds(lea(s, sbase));
+                    const uint32_t s = u[i] = sad(u[i], u[(i + 1) & 7]);   /* feeds itself: not loop-invariant; <= 1020, then <= 258 */ float ww = lds(lea(s, sbase));
                     const int j = i & 1;
                     p[2 * j] = fma2(p[4 + j], pk(ww, ww), p[2 * j]); p[2 * j + 1] = fma2(p[6 + j], pk(ww, ww), p[2 * j + 1]);
                 }
+                if (MODE == 17) { u[i] = sad(u[i], u[(i + 1) & 7]); f[i] = ffma(f[i], w, f[(i + 1) & 7]); f[(i + 2) & 7] = ffma(f[(i + 2) & 7], w, f[(i + 3) & 7]); }
+                if (MODE == 18) { u[i] = sad(u[i], u[(i + 1) & 7]); f[i] = ffma(f[i], w, f[(i + 1) & 7]); f[(i + 2) & 7] = ffma(f[(i + 2) & 7], w, f[(i + 3) & 7]);
+                                  f[(i + 4) & 7] = ffma(f[(i + 4) & 7], w, f[(i + 5) & 7]); f[(i + 6) & 7] = ffma(f[(i + 6) & 7], w, f[(i + 7) & 7]); }
+                if (MODE == 19) { u[i] = u[i] * 3 + u[(i + 1) & 7]; f[i] = ffma(f[i], w, f[(i + 1) & 7]); f[(i + 2) & 7] = ffma(f[(i + 2) & 7], w, f[(i + 3) & 7]); }
+                if (MODE == 20) { u[i] = prmt(u[i], 0x7540 + (i & 3)); f[i] = ffma(f[i], w, f[(i + 1) & 7]); f[(i + 2) & 7] = ffma(f[(i + 2) & 7], w, f[(i + 3) & 7]); }
+                if (MODE == 21) { u[i] = lea(u[i], u[(i + 1) & 7]); f[i] = ffma(f[i], w, f[(i + 1) & 7]); }
+                if (MODE == 22) { f[i] = lds(sbase + ((__float_as_uint(f[i]) >> 3) & 0x3f80)); f[(i + 2) & 7] = ffma(f[(i + 2) & 7], w, f[(i + 3) & 7]); f[(i + 4) & 7] = ffma(f[(i + 4) & 7], w, f[(i + 5) & 7]);
+                                  f[(i + 6) & 7] = ffma(f[(i + 6) & 7], w, f[(i + 7) & 7]); f[(i + 1) & 7] = ffma(f[(i + 1) & 7], w, f[(i + 3) & 7]); }
+                if (MODE == 23) { f[i] = lds(sbase + ((__float_as_uint(f[i]) >> 3) & 0x3f80)); u[i] = sad(u[i], u[(i + 1) & 7]); u[(i + 2) & 7] = sad(u[(i + 2) & 7], u[(i + 3) & 7]); }
+                if (MODE == 24) f[i] = ffma(f[i], w, f[(i + 2) & 7]);                 // register-bank test: sources two registers apart
+                if (MODE == 25) f[i] = ffma(f[i], f[(i + 4) & 7], f[(i + 2) & 7]);   // three sources of one parity
+                if (MODE == 26) f[i] = ffma(f[i], f[(i + 3) & 7], f[(i + 2) & 7]);   // two of one parity, one of the other
                 if (MODE == 15) f[i] = fmul(f[i], w);
                 if (MODE == 16) u[i] = u[i] * 3 + u[(i + 1) & 7];   // IMAD
             }
@@ -104,6 +116,14 @@ int main()
         run<11>("tap folded packed: SAD LEA LDS 2FFMA2", 5, nw); run<14>("tap folded packed, 2 px interleaved", 5, nw);
         run<10>("tap private packed: SAD LEA LDS FMUL 2FFMA2", 6, nw);
         run<12>("tap private scalar: SAD LEA LDS FMUL FADD 3FFMA", 8, nw);
+        run<24>("FFMA r, same-parity r, w (reuse)", 1, nw); run<25>("FFMA, three sources of one register parity", 1, nw); run<26>("FFMA, sources 2 + 1 by parity", 1, nw);
+        run<17>("mix: VABSDIFF4 + 2 FFMA (separate pipes: 3, shared: 4)", 3, nw);
+        run<18>("mix: VABSDIFF4 + 4 FFMA (separate: 5, shared: 6)", 5, nw);
+        run<19>("mix: IMAD + 2 FFMA", 3, nw);
+        run<20>("mix: PRMT + 2 FFMA", 3, nw);
+        run<21>("mix: LEA + FFMA", 2, nw);
+        run<22>("mix: LDS + SHF/LOP address + 4 FFMA", 5, nw);
+        run<23>("mix: LDS + address + 2 VABSDIFF4", 3, nw);
     }
     return 0;
 }
