@@ -512,6 +512,45 @@ def main():
                     "CPU: the reference's loop over 64 squares with cv2 (its default threads), 2 frames"}
         sth.free()
 
+    # ---- the other half of SURVEY 8f rank 4: GameSession._draw_interface on the device (csrc/cvb_overlay.cu)
+    if rank == 0 and not args.no_extras and world == 1:
+        from chessboard_vision_b200.overlay import BoardOverlay
+        Sb = 800                                                     # the reference's board size (game_session.py:94)
+        start = {}
+        for f_, s_ in enumerate("RNBQKBNR"):
+            start[(f_, 0)] = s_; start[(f_, 1)] = "P"; start[(f_, 6)] = "p"; start[(f_, 7)] = s_.lower()
+        ov_state = dict(noise_active=True, last_move=((4, 1), (4, 3)), lifted=(6, 7), radar=[(5, 5), (7, 5)], pieces=start,
+                        white_to_move=False, fps=30.0)
+        board_img = np.ascontiguousarray(synth.frame_batch(1, Sb, Sb, "board", 3)[0])
+        dl = BoardOverlay.display_list(Sb, **ov_state)
+        ops_o, n_o, masks_o = dl.pack()
+        boards_dev = eng.upload(np.stack([board_img] * 16))
+        run_ov = lambda k: [eng.overlay(boards_dev, ops_o, n_o, masks_o) for _ in range(k)]
+        run_ov(3)
+        ms_ov, _ = timed(run_ov, 10)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            BoardOverlay.display_list(Sb, **ov_state).pack()
+        host_list_ms = (time.perf_counter() - t0) * 1e3 / 20
+        cpu_ov = same = None
+        try:
+            from oracle import overlay as ov_oracle
+            ref_img = ov_oracle.draw_interface_cv2(board_img.copy(), Sb, **ov_state)
+            same = bool(np.array_equal(eng.overlay(board_img, ops_o, n_o, masks_o), ref_img))
+            t0 = time.perf_counter()
+            for _ in range(10):
+                ov_oracle.draw_interface_cv2(board_img.copy(), Sb, **ov_state)
+            cpu_ov = (time.perf_counter() - t0) * 1e3 / 10
+        except ImportError:
+            pass
+        extras["next_board_overlay"] = {
+            "device_us_per_board": ms_ov / 10 / 16 * 1e3, "display_list_ops": n_o, "host_list_build_ms": host_list_ms,
+            "cpu_reference_ms_per_board": cpu_ov, "identical_to_cv2_sequence": same,
+            "what": "GameSession._draw_interface (grid, noise tint + text, last move, lifted square, 2 radar discs, 32 piece "
+                    "letters, status texts) on an 800 x 800 warped board: one k_overlay launch per board batch of 16 "
+                    "(list upload included); CPU: the same cv2 call sequence (oracle/overlay.py)"}
+        boards_dev.free()
+
     # ---- parity beside the throughput number: the reference's cv2 / numpy call sequence against the
     # CUDA path on (previous, current) pairs of the very frame kinds that are timed: Otsu T, mask per pixel, change flags
     parity = None

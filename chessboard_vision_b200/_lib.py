@@ -79,6 +79,17 @@ class HoughResult(C.Structure):
 
 assert C.sizeof(HoughParams) == 56 and C.sizeof(HoughSquare) == 40 and C.sizeof(HoughResult) == 272
 
+OV_RECT, OV_CIRCLE, OV_STAMP = 0, 1, 2
+
+
+class OverlayOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32),
+                ("color", C.c_uint8 * 4), ("alpha", C.c_float), ("beta", C.c_float), ("group", C.c_int32),
+                ("aux_ofs", C.c_uint32)]
+
+
+assert C.sizeof(OverlayOp) == 40
+
 SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE = 1, 2, 4, 8, 16
 PLANE_PD_REF, PLANE_CD_MEAN, PLANE_CD_VAR, PLANE_PD_CUR, PLANE_FLAGS = 0, 1, 2, 3, 4
 FMT_BGR, FMT_YUY2, FMT_NV12 = 0, 1, 2
@@ -131,6 +142,7 @@ SYMBOLS = [
     ("cvb_warp_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     ("cvb_warp_rot180_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _P]),
     ("cvb_rotate_dev", _I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    ("cvb_overlay_dev", _I, [_P, _P, _I, _I, _I, _P, _I, _P, _SZ]),
     ("cvb_gaussian_sigma_dev", _I, [_P, _P, _I, _I, _I, _I, _D, _P]),
     ("cvb_dilate_dev", _I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     ("cvb_contour_mask_dev", _I, [_P, _P, _I, _I, _I, _P]),

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 static_assert(sizeof(cvb_color_profile) == 48 && sizeof(cvb_enhance_params) == 96, "ABI struct layout (see _lib.py)");
+static_assert(sizeof(cvb_overlay_op) == 40, "ABI struct layout (see _lib.py)");
 static thread_local char g_err[512] = "";
 
 void cvb_set_error(const char *fmt, ...)
@@ -929,6 +930,86 @@ int cvb_pipeline_dev(cvb_handle *h, const uint8_t *bgr, int n, int H, int W, con
                            otsu_t, warped, stats);
 }
 
+// ---- board overlay ---------------------------------------------------------------------------
+// half widths of the rows dy = 0..r of a filled circle: the spans drawing.cpp's Circle() fills (midpoint algorithm)
+static void circle_half_widths(int r, uint16_t *half)
+{
+    for (int i = 0; i <= r; ++i) half[i] = 0;
+    int err = 0, dx = r, dy = 0, plus = 1, minus = (r << 1) - 1;
+    while (dx >= dy) {
+        if (dx > half[dy]) half[dy] = (uint16_t)dx;      // rows +-dy are filled over +-dx
+        if (dy > half[dx]) half[dx] = (uint16_t)dy;      // rows +-dx over +-dy
+        ++dy; err += plus; plus += 2;
+        const int mask = (err <= 0) - 1;
+        err -= minus & mask; dx += mask; minus -= mask & 2;
+    }
+}
+
+int cvb_overlay_dev(cvb_handle *h, uint8_t *bgr, int n, int H, int W, const cvb_overlay_op *ops, int n_ops,
+                    const uint8_t *masks, size_t mask_bytes)
+{
+    REQ_H(h); REQ_IMG(n, H, W);
+    CVB_REQUIRE(bgr, "null image pointer");
+    CVB_REQUIRE(n_ops >= 0 && (n_ops == 0 || ops), "null display list");
+    if (n_ops == 0) return CVB_OK;
+    // validate, lay out [ops][circle tables][masks] in one staging vector
+    std::vector<cvb_overlay_op> list(ops, ops + n_ops);
+    std::map<int, uint32_t> circle_ofs;
+    std::vector<uint16_t> tables;
+    for (int i = 0; i < n_ops; ++i) {
+        cvb_overlay_op &o = list[i];
+        CVB_REQUIRE(o.kind >= CVB_OV_RECT && o.kind <= CVB_OV_STAMP, "overlay op %d: unknown kind %d", i, o.kind);
+        CVB_REQUIRE(o.alpha == o.alpha && o.beta == o.beta, "overlay op %d: NaN weight", i);
+        const int lim = 1 << 20;
+        CVB_REQUIRE(o.x0 > -lim && o.x0 < lim && o.y0 > -lim && o.y0 < lim && o.x1 > -lim && o.x1 < lim && o.y1 > -lim && o.y1 < lim,
+                    "overlay op %d: coordinate out of range", i);
+        if (o.kind == CVB_OV_RECT) {                       // cv2.rectangle / cv2.line accept the corners in any order
+            if (o.x0 > o.x1) std::swap(o.x0, o.x1);
+            if (o.y0 > o.y1) std::swap(o.y0, o.y1);
+        } else if (o.kind == CVB_OV_CIRCLE) {
+            CVB_REQUIRE(o.x1 >= 0 && o.x1 <= 16384, "overlay op %d: circle radius %d", i, o.x1);
+            auto it = circle_ofs.find(o.x1);
+            if (it == circle_ofs.end()) {
+                it = circle_ofs.emplace(o.x1, (uint32_t)(tables.size() * sizeof(uint16_t))).first;
+                tables.resize(tables.size() + o.x1 + 1);
+                circle_half_widths(o.x1, tables.data() + it->second / sizeof(uint16_t));
+            }
+            o.aux_ofs = it->second;
+        } else {
+            CVB_REQUIRE(o.x1 >= 1 && o.y1 >= 1 && o.x1 <= 32768 && o.y1 <= 32768, "overlay op %d: stamp size %d x %d", i, o.x1, o.y1);
+            const size_t need = (size_t)o.aux_ofs + (size_t)((o.x1 + 7) >> 3) * o.y1;
+            CVB_REQUIRE(masks && need <= mask_bytes, "overlay op %d: stamp mask outside the %zu mask bytes", i, mask_bytes);
+        }
+        if (o.group != 0 && i > 0 && list[i - 1].group == o.group)
+            CVB_REQUIRE(memcmp(o.color, list[i - 1].color, 3) == 0 && o.alpha == list[i - 1].alpha && o.beta == list[i - 1].beta,
+                        "overlay op %d: ops of one group share color, alpha and beta", i);
+    }
+    for (int i = 0; i < n_ops; ++i)                       // a group id is not reused by a later, separate run of ops
+        if (list[i].group != 0 && i > 0 && list[i - 1].group != list[i].group)
+            for (int j = 0; j < i - 1; ++j)
+                CVB_REQUIRE(list[j].group != list[i].group, "overlay op %d: group %d is not consecutive", i, list[i].group);
+    const size_t ops_bytes = sizeof(cvb_overlay_op) * (size_t)n_ops;
+    const size_t tab_bytes = (tables.size() * sizeof(uint16_t) + 15) & ~(size_t)15;
+    for (auto &o : list) if (o.kind == CVB_OV_STAMP) o.aux_ofs += (uint32_t)tab_bytes;
+    std::vector<uint8_t> stage(ops_bytes + tab_bytes + mask_bytes);
+    memcpy(stage.data(), list.data(), ops_bytes);
+    if (!tables.empty()) memcpy(stage.data() + ops_bytes, tables.data(), tables.size() * sizeof(uint16_t));
+    if (mask_bytes) memcpy(stage.data() + ops_bytes + tab_bytes, masks, mask_bytes);
+    WS(ws_overlay, uint8_t, stage.size(), d);
+    CVB_CHECK_CUDA(cudaMemcpyAsync(d, stage.data(), stage.size(), cudaMemcpyHostToDevice, h->stream));
+    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));     // `stage` dies at return
+    const cvb_overlay_op *d_ops = reinterpret_cast<const cvb_overlay_op *>(d);
+    const int cap = cvb_overlay_max_ops();
+    for (int first = 0; first < n_ops;) {                 // longer lists: slices that do not cut a group
+        int end = std::min(n_ops, first + cap);
+        while (end < n_ops && end > first && list[end].group != 0 && list[end].group == list[end - 1].group) --end;
+        CVB_REQUIRE(end > first, "overlay: a group of more than %d ops", cap);
+        CVB_TRY(launch_overlay(h, bgr, n, H, W, d_ops + first, end - first, d + ops_bytes));
+        first = end;
+    }
+    return CVB_OK;
+}
+
 size_t cvb_frame_bytes(int format, int H, int W) { return cvb_host_frame_bytes(format, H, W); }
 
 int cvb_cvt_to_bgr_dev(cvb_handle *h, const uint8_t *src, int format, int n, int H, int W, uint8_t *bgr)
@@ -1049,7 +1130,7 @@ long long cvb_debug_bounds_violations(cvb_handle *h, int *first_line)
 #ifdef CVB_DEBUG_BOUNDS
     if (!h || cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -2;
     void (*tus[])(unsigned long long *, int *) = {cvb_bounds_enhance, cvb_bounds_fused2, cvb_bounds_grid, cvb_bounds_canny,
-                                                  cvb_bounds_hough, cvb_bounds_ingest};
+                                                  cvb_bounds_hough, cvb_bounds_ingest, cvb_bounds_overlay};
     unsigned long long total = 0;
     for (auto fn : tus) {
         unsigned long long n = 0; int line = 0;

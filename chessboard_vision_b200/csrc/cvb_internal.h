@@ -95,6 +95,7 @@ struct cvb_handle {
     // Hough: staged per-square geometry (content-compared), select bytes, results
     std::vector<cvb_hough_square> hough_cache;
     DevBuf ws_hough_sq, ws_hough_sel, ws_hough_res;
+    DevBuf ws_overlay;          // display list + circle span tables + stamp masks of the last cvb_overlay_dev call
     void *pinned = nullptr;
     size_t pinned_cap = 0;
 };
@@ -163,10 +164,14 @@ int launch_threshold(cvb_handle *h, const uint8_t *src, int n, long npx, const i
 void cvb_bounds_enhance(unsigned long long *, int *); void cvb_bounds_fused2(unsigned long long *, int *);
 void cvb_bounds_grid(unsigned long long *, int *); void cvb_bounds_canny(unsigned long long *, int *);
 void cvb_bounds_hough(unsigned long long *, int *); void cvb_bounds_ingest(unsigned long long *, int *);
+void cvb_bounds_overlay(unsigned long long *, int *);
 
 // ---- cvb_ingest.cu ------------------------------------------------------------------------
 size_t cvb_host_frame_bytes(int format, int H, int W);
 int launch_yuv_to_bgr(cvb_handle *h, const uint8_t *src, int format, int n, int H, int W, uint8_t *bgr);
+// cvb_overlay.cu: one slice (<= cvb_overlay_max_ops() ops) of a display list, ops and aux resident on the device
+int cvb_overlay_max_ops();
+int launch_overlay(cvb_handle *h, uint8_t *bgr, int n, int H, int W, const cvb_overlay_op *d_ops, int n_ops, const uint8_t *d_aux);
 
 // ---- cvb_canny.cu -------------------------------------------------------------------------
 int launch_canny(cvb_handle *h, const uint8_t *gray, int n, int H, int W, double low_thresh, double high_thresh, uint8_t *edges);

@@ -491,6 +491,18 @@ class Engine:
         check(self.lib.cvb_rotate_dev(self.h, src.ptr, n, H, W, ch, int(code), dst.ptr))
         return self._out(dst, tmp, [src] if tmp else [])
 
+    def overlay(self, img, ops, n_ops, masks=b""):
+        """Apply a display list (ctypes array of _lib.OverlayOp, first n_ops used) to (H,W,3) / (n,H,W,3) u8 images:
+        cvb_overlay_dev.  A DevArray is drawn in place and returned; a NumPy image is uploaded, drawn and returned
+        as a new array."""
+        single, n, H, W = _as_batch(img, 3)
+        dev, tmp = self._in(img)
+        masks = bytes(masks)
+        mbuf = (C.c_uint8 * max(1, len(masks))).from_buffer_copy(masks or b"\0")
+        check(self.lib.cvb_overlay_dev(self.h, dev.ptr, n, H, W, C.cast(ops, C.c_void_p) if n_ops else None, int(n_ops),
+                                       C.cast(mbuf, C.c_void_p), len(masks)))
+        return self._out(dev, tmp)
+
     # -- Canny / grid refinement (calibration time) ----------------------------------------------
     def canny(self, gray, low=50, high=150):
         return self._canny(gray, low, high)

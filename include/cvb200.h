@@ -359,6 +359,35 @@ int cvb_pipeline(cvb_handle *h, const uint8_t *bgr, int n, int H, int W,
  * reference has no counterpart (its arrays are bounds-checked by NumPy, e.g. grid_extractor.py:46). */
 long long cvb_debug_bounds_violations(cvb_handle *h, int *first_line);
 
+/* ---- board overlay (second half) ---------------------------------- */
+/* GameSession._draw_interface (game_session.py:293-388) draws the grid, the tints and highlights
+ * and the piece letters on the warped board with cv2.line / rectangle / circle / putText and
+ * `overlay = vis.copy(); <shape>; cv2.addWeighted(overlay, a, vis, b, 0, vis)`.  The same
+ * drawing as a display list applied in order on a DEVICE image, pixel-exactly:
+ *   RECT    inclusive corners (x0,y0)-(x1,y1), clipped: cv2.rectangle(.., -1), axis-aligned
+ *           cv2.line of thickness 1, `overlay[:] = colour`       game_session.py:301-312,326-336,346
+ *   CIRCLE  centre (x0,y0), radius x1: cv2.circle(.., -1)        game_session.py:356
+ *   STAMP   a w x h (x1, y1) 1-bit mask with its top-left at (x0,y0): what cv2.putText sets
+ *           (rasterised once per string by the caller)            game_session.py:316,375-378,382,385
+ * alpha == 1 && beta == 0 stores `color`; otherwise dst = saturate(rint(fma(color, alpha,
+ * dst * beta))), OpenCV's addWeighted for 8-bit images.  Ops that share a non-zero `group` are
+ * shapes drawn on ONE overlay copy (game_session.py:322-338): a pixel is blended once per group;
+ * they must be consecutive and share color / alpha / beta. */
+enum { CVB_OV_RECT = 0, CVB_OV_CIRCLE = 1, CVB_OV_STAMP = 2 };
+typedef struct {
+    int32_t kind;
+    int32_t x0, y0, x1, y1;
+    uint8_t color[4];          /* B, G, R, 0 */
+    float alpha, beta;
+    int32_t group;             /* 0: on its own */
+    uint32_t aux_ofs;          /* STAMP: byte offset of its mask in `masks` (rows of (w + 7) / 8 bytes, bit x & 7 of
+                                  byte x >> 3); set by the library for CIRCLE */
+} cvb_overlay_op;
+/* bgr: DEVICE, n images of H x W x 3, drawn in place (every image gets the same list);
+ * ops / masks: HOST */
+int cvb_overlay_dev(cvb_handle *h, uint8_t *bgr, int n, int H, int W, const cvb_overlay_op *ops, int n_ops,
+                    const uint8_t *masks, size_t mask_bytes);
+
 /* ---- camera ingest ---------------------------------------------- */
 /* play_lichess.py:16-18,45 / game_session.py:99,113 receive BGR frames from
  * cv2.VideoCapture.read(), i.e. after OpenCV has converted the camera's native YUV on the
