@@ -390,14 +390,22 @@ def main():
     my_frames = [n]        # frames this rank feeds per e2e step (equal shares until the feed rates are known)
 
     def run_e2e(k):
+        # the public host-buffer calls of a capture loop: submit a batch (H2D + kernels + D2H of the per-square results
+        # enqueued), then collect the PREVIOUS batch's results while this one runs -- one batch in flight ahead, so the
+        # first copy of a batch overlaps the kernels of the one before.  Everything submitted is waited for before the
+        # function returns.  A share above the n frames of the pinned batch wraps around (a second call on the first
+        # frames, their state in the upper stream slots).
+        pending = []
         for _ in range(k):
-            # the public host-buffer call: H2D + kernels + D2H of per-square results; a share above the n frames of the
-            # pinned batch wraps around (a second call on the first frames, their state in the upper stream slots)
             done = 0
             while done < my_frames[0]:
                 cnt = min(n, my_frames[0] - done)
-                eng.pipeline(host[:cnt], M, rects, pp, state, stream0=done, fmt=args.ingest)
+                pending.append(eng.pipeline_submit(host[:cnt], M, rects, pp, state, stream0=done, fmt=args.ingest))
+                if len(pending) > 1:
+                    eng.pipeline_wait(pending.pop(0))
                 done += cnt
+        while pending:
+            eng.pipeline_wait(pending.pop(0))
 
     sampler = ClockSampler(device) if rank == 0 else None
     if sampler:
@@ -467,7 +475,14 @@ def main():
                 hn = eng.pinned((n,) + nat.shape[1:])
                 for i in range(n):
                     hn[i] = nat[i % UNIQUE]
-                run_n = lambda k: [eng.pipeline(hn, M, rects, pp, state, fmt=fmt) for _ in range(k)]
+                def run_n(k, hn=hn, fmt=fmt):
+                    pend = []
+                    for _ in range(k):
+                        pend.append(eng.pipeline_submit(hn, M, rects, pp, state, fmt=fmt))
+                        if len(pend) > 1:
+                            eng.pipeline_wait(pend.pop(0))
+                    while pend:
+                        eng.pipeline_wait(pend.pop(0))
                 run_n(3)
                 ms_n, _ = timed(run_n, 8)
                 extras["e2e_ingest_" + fmt] = {"value": n * 8 / (ms_n / 1e3), "unit": "frames/s", "ms_per_step": ms_n / 8,
@@ -633,8 +648,9 @@ def main():
                        "sharding": "equal" if not e2e_shares or len(set(e2e_shares)) == 1 else "N x %d frames per step, each rank's share proportional to the "
                                    "host->device rate it sustained in the warm-up (the GPUs of this box do not share the host "
                                    "path equally); no data-path collective" % n,
-                       "api": "Engine.pipeline -> cvb_pipeline_fmt (pinned host frames in, per-square statistics + Otsu "
-                              "thresholds out)"},
+                       "api": "Engine.pipeline_submit / pipeline_wait -> cvb_pipeline_submit / cvb_pipeline_wait (pinned host "
+                              "frames in, per-square statistics + Otsu thresholds out of EVERY step, one batch in flight ahead "
+                              "as in a capture loop; all K steps are submitted and completed inside the timed region)"},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "parity": parity, "extras": extras}
         emit(out)

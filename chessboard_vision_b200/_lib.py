@@ -168,6 +168,9 @@ SYMBOLS = [
     ("cvb_frame_bytes", _SZ, [_I, _I, _I]),
     ("cvb_cvt_to_bgr_dev", _I, [_P, _P, _I, _I, _I, _I, _P]),
     ("cvb_pipeline_fmt", _I, [_P, _P, _I, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    ("cvb_pipeline_submit", _I, [_P, _P, _I, _I, _I, _I, C.POINTER(PipelineParams), _P, _I, _P, _I, _P, _P, _I, _P, _P,
+                                 C.POINTER(C.c_uint64)]),
+    ("cvb_pipeline_wait", _I, [_P, C.c_uint64]),
 ]
 
 _lib = None

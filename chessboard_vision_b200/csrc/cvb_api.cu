@@ -116,12 +116,13 @@ void cvb_destroy(cvb_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_raw, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
+    DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
                       &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks,
-                      &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res};
+                      &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res, &h->ws_stage, &h->ws_overlay};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    for (cudaEvent_t e : h->ev_ticket) if (e) cudaEventDestroy(e);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_color) cudaFree(h->d_color);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -432,10 +433,10 @@ static int analysis_tail(cvb_handle *h, const uint8_t *src, const int32_t *minma
     }
     CVB_TRY(launch_finish(h, src, n, H, W, minmax, enhanced, gray, blurred, want_bin ? hist : nullptr));
     if (want_bin) {
-        // The Otsu scan is a chain of 256 dependent f64 divisions (~40 us whatever the batch).  For small batches the
+        // The Otsu scan is a chain of 256 dependent f64 divisions (~40 us whatever the batch).  For batches up to a chunk the
         // whole-path entry points fork it, with the mask, onto a second stream: the warp and the square kernel that
         // follow on the main stream need neither (they read the enhanced frame), join_tail() brings the streams together.
-        const bool fork = h->fork_tail && n <= 16;
+        const bool fork = h->fork_tail && n <= 64;     // single frames up to the chunks of the host-buffer pipeline
         cudaStream_t main_stream = h->stream;
         if (fork) {
             if (!h->aux_stream) {
@@ -1027,9 +1028,13 @@ int cvb_cvt_to_bgr_dev(cvb_handle *h, const uint8_t *src, int format, int n, int
 // stream while chunk k is being processed (two input buffers), so the PCIe copy and the kernels
 // overlap when the host memory is page-locked.  Frames arrive in `format`; YUV frames are converted
 // to BGR on the device (cvb_ingest.cu), so only their 2 or 1.5 bytes per pixel cross PCIe.
-int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W, const cvb_pipeline_params *p,
-                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state,
-                     int stream0, int32_t *otsu_t, cvb_square_stats *stats)
+// wait == false: everything is enqueued (copies in, kernels, copies out) and the call returns; cvb_pipeline_wait joins.
+// The staging buffers (ws_stage) belong to this function alone, so the only hazards on them are its own earlier chunks,
+// of this call or of the previous one: the per-buffer ev_done events.  The first copy of a call therefore overlaps the
+// kernels of the previous call.
+static int pipeline_fmt_impl(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W, const cvb_pipeline_params *p,
+                             const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select,
+                             cvb_state *state, int stream0, int32_t *otsu_t, cvb_square_stats *stats, bool wait)
 {
     CVB_TRY(pipeline_check(h, frames, n, H, W, p, M9, n_mats, rects));
     CVB_REQUIRE(n_sq >= 1, "no squares");
@@ -1064,9 +1069,8 @@ int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, in
         }
     }
     // two staging buffers of one chunk in the arrival format; YUV chunks are converted into one BGR buffer
-    DevBuf &stage = format == CVB_FMT_BGR ? h->ws_in : h->ws_raw;
     uint8_t *d_in = nullptr, *d_bgr = nullptr;
-    CVB_TRY(cvb_ws(h, stage, fin * chunk * 2, (void **)&d_in));
+    CVB_TRY(cvb_ws(h, h->ws_stage, fin * chunk * 2, (void **)&d_in));
     if (format != CVB_FMT_BGR) CVB_TRY(cvb_ws(h, h->ws_in, fb * chunk, (void **)&d_bgr));
     WS(ws_stats, cvb_square_stats, (size_t)n * n_sq, d_stats);
     WS(ws_otsu_all, int32_t, n, d_otsu);
@@ -1085,14 +1089,18 @@ int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, in
         CVB_TRY(cvb_ws(h, h->ws_sharp, fb * chunk, &t)); CVB_TRY(cvb_ws(h, h->ws_blur, npx * chunk, &t));
         CVB_TRY(cvb_ws(h, h->ws_lab, fb * chunk, &t));
     }
-    // the copy stream must not start before earlier work on the compute stream that reads the staging buffers is done
-    CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[0], h->stream));
-    CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[0], 0));
+    if (h->stage_layout != fin * chunk) {
+        // other buffer boundaries than the previous call used: both buffers are free only when all earlier kernels are
+        for (int i = 0; i < 2; ++i) CVB_CHECK_CUDA(cudaEventRecord(h->ev_done[i], h->stream));
+        h->stage_layout = fin * chunk;
+    }
     int k = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, ++k) {
         const int cnt = std::min(chunk, n - f0), b = k & 1;
         uint8_t *buf = d_in + (size_t)b * chunk * fin;
-        if (k >= 2) CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+        // buffer b is free once the last kernel that read it is done: an earlier chunk of this call or of the previous
+        // one (waiting on an event that was never recorded returns at once)
+        CVB_CHECK_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
         CVB_CHECK_CUDA(cudaMemcpyAsync(buf, frames + (size_t)f0 * fin, fin * cnt, cudaMemcpyHostToDevice, h->copy_stream));
         CVB_CHECK_CUDA(cudaEventRecord(h->ev_copy[b], h->copy_stream));
         CVB_CHECK_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
@@ -1112,7 +1120,37 @@ int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, in
         CVB_CHECK_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(cvb_square_stats) * (size_t)n * n_sq,
                                        cudaMemcpyDeviceToHost, h->stream));
     if (otsu_t) CVB_CHECK_CUDA(cudaMemcpyAsync(otsu_t, d_otsu, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-    CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    if (wait) CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    return CVB_OK;
+}
+
+int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W, const cvb_pipeline_params *p,
+                     const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state,
+                     int stream0, int32_t *otsu_t, cvb_square_stats *stats)
+{
+    return pipeline_fmt_impl(h, frames, format, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, otsu_t, stats, true);
+}
+
+int cvb_pipeline_submit(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W, const cvb_pipeline_params *p,
+                        const double *M9, int n_mats, const cvb_rect *rects, int n_sq, const uint8_t *select, cvb_state *state,
+                        int stream0, int32_t *otsu_t, cvb_square_stats *stats, uint64_t *ticket)
+{
+    CVB_TRY(pipeline_fmt_impl(h, frames, format, n, H, W, p, M9, n_mats, rects, n_sq, select, state, stream0, otsu_t, stats, false));
+    const uint64_t seq = ++h->tickets;
+    cudaEvent_t &ev = h->ev_ticket[seq % CVB_TICKET_RING];
+    if (!ev) CVB_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CVB_CHECK_CUDA(cudaEventRecord(ev, h->stream));
+    if (ticket) *ticket = seq;
+    return CVB_OK;
+}
+
+int cvb_pipeline_wait(cvb_handle *h, uint64_t ticket)
+{
+    REQ_H(h);
+    CVB_REQUIRE(ticket <= h->tickets, "ticket %llu was never issued by this handle", (unsigned long long)ticket);
+    // a slot of the ring that a later submission re-used marks a later point of the same stream: waiting there is enough
+    if (ticket == 0 || h->tickets - ticket >= CVB_TICKET_RING) CVB_CHECK_CUDA(cudaStreamSynchronize(h->stream));
+    else CVB_CHECK_CUDA(cudaEventSynchronize(h->ev_ticket[ticket % CVB_TICKET_RING]));
     return CVB_OK;
 }
 

@@ -62,6 +62,7 @@ struct RectCache {
     size_t mask_bytes = 0;
 };
 
+constexpr unsigned CVB_TICKET_RING = 8;
 struct cvb_handle {
     RectCache rect_cache;
     std::vector<double> mat_cache;
@@ -79,7 +80,7 @@ struct cvb_handle {
     float *d_color = nullptr;
     double color_sigma = -1.0, space_sigma = -1.0;
     // grow-only scratch
-    DevBuf ws_lab, ws_prof, ws_in, ws_raw, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
+    DevBuf ws_lab, ws_prof, ws_in, ws_sharp, ws_enh, ws_gray, ws_blur, ws_bin, ws_warp, ws_plane, ws_plane2;
     DevBuf ws_hist, ws_lut, ws_minmax, ws_ohist, ws_otsu, ws_otsu_all, ws_stats, ws_rects, ws_select, ws_mats;
     // host-buffer pipeline: copy stream + double-buffer events, frames per chunk
     // forked tail of the analysis stage (Otsu scan + mask) for small batches: it runs on aux_stream beside the warp and
@@ -89,12 +90,16 @@ struct cvb_handle {
     bool fork_tail = false, tail_pending = false;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint64_t tickets = 0;       // cvb_pipeline_submit: submissions so far; ev_ticket[seq % ring] marks the end of submission seq
+    cudaEvent_t ev_ticket[8] = {};
+    size_t stage_layout = 0;    // bytes per staging buffer of the last host-buffer pipeline call
     int chunk_frames = 0;       // frames per chunk of the host-buffer pipeline; 0 = chosen per call (cvb_pipeline_fmt)
     // mask cache for square shapes: (h<<16|w) -> offset into ws_masks
     DevBuf ws_masks;
     // Hough: staged per-square geometry (content-compared), select bytes, results
     std::vector<cvb_hough_square> hough_cache;
     DevBuf ws_hough_sq, ws_hough_sel, ws_hough_res;
+    DevBuf ws_stage;            // the two chunk staging buffers of the host-buffer pipeline (its own: see pipeline_fmt_impl)
     DevBuf ws_overlay;          // display list + circle span tables + stamp masks of the last cvb_overlay_dev call
     void *pinned = nullptr;
     size_t pinned_cap = 0;

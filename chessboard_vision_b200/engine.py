@@ -729,6 +729,31 @@ class Engine:
                                         stats.ctypes.data))
         return t, stats
 
+    def pipeline_submit(self, frames, M, rects, params, state=None, stream0=0, select=None, fmt="bgr"):
+        """`pipeline` without the wait: returns a ticket; `pipeline_wait(ticket)` -> (otsu_t, stats).  Submit batch k+1
+        before waiting for batch k and its first host->device copy runs beside the kernels of batch k.  `frames` must
+        be a C-contiguous uint8 array (pinned: Engine.pinned) that is left alone until the wait."""
+        if not (isinstance(frames, np.ndarray) and frames.dtype == np.uint8 and frames.flags.c_contiguous):
+            raise ValueError("pipeline_submit: frames must be a C-contiguous uint8 array (it is read after the call returns)")
+        n, H, W = self._frame_geometry(frames, fmt)
+        M = np.ascontiguousarray(M, np.float64)
+        n_mats = 1 if M.ndim == 2 else M.shape[0]
+        ra = _rect_array(rects)
+        stats = np.empty((n, len(rects)), STATS_DTYPE); t = np.empty(n, np.int32)
+        sel = np.ascontiguousarray(select, np.uint8) if select is not None else None
+        ticket = C.c_uint64(0)
+        check(self.lib.cvb_pipeline_submit(self.h, frames.ctypes.data, _lib.FORMATS[fmt], n, H, W, C.byref(params),
+                                           M.ctypes.data, n_mats, C.cast(ra, C.c_void_p), len(rects),
+                                           sel.ctypes.data if sel is not None else None,
+                                           state.ptr if state is not None else None, int(stream0), t.ctypes.data,
+                                           stats.ctypes.data, C.byref(ticket)))
+        return (ticket.value, t, stats, frames, M, ra, sel)     # keeps every buffer the enqueued work touches alive
+
+    def pipeline_wait(self, ticket):
+        """-> (otsu_t, stats) of that submission, complete"""
+        check(self.lib.cvb_pipeline_wait(self.h, ticket[0]))
+        return ticket[1], ticket[2]
+
     def pipeline_dev(self, src, M, rects, params, state=None, stream0=0, select=None, enhanced=None, gray=None,
                      binary=None, otsu_t=None, warped=None, stats=None):
         n, H, W = src.shape[0], src.shape[1], src.shape[2]

@@ -410,6 +410,22 @@ int cvb_pipeline_fmt(cvb_handle *h, const uint8_t *frames, int format, int n, in
                      const cvb_rect *rects, int n_sq, const uint8_t *select,
                      cvb_state *state, int stream0,
                      int32_t *otsu_t, cvb_square_stats *stats);
+/* The same call split in two for a caller that receives batches continuously (a capture loop:
+ * game_session.py:113 / play_lichess.py:45 per frame): cvb_pipeline_submit enqueues the copies
+ * in, the kernels and the copies out, writes a ticket (> 0) and returns; cvb_pipeline_wait(h,
+ * ticket) returns when that submission is complete (ticket 0: everything submitted so far).
+ * Submitting batch k+1 before waiting for batch k lets its first host->device copy run beside
+ * the kernels of batch k; batches execute in submission order, so per-stream state evolves as
+ * with cvb_pipeline_fmt.  `frames`, `otsu_t` and `stats` must stay valid (and `frames`
+ * unmodified) until the wait; use a different result buffer per batch in flight.  Pinned host
+ * memory (cvb_host_alloc) is needed for the overlap. */
+int cvb_pipeline_submit(cvb_handle *h, const uint8_t *frames, int format, int n, int H, int W,
+                        const cvb_pipeline_params *p,
+                        const double *M9, int n_mats,
+                        const cvb_rect *rects, int n_sq, const uint8_t *select,
+                        cvb_state *state, int stream0,
+                        int32_t *otsu_t, cvb_square_stats *stats, uint64_t *ticket);
+int cvb_pipeline_wait(cvb_handle *h, uint64_t ticket);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -85,3 +85,42 @@ def test_pipeline_on_native_frames_equals_pipeline_on_converted_frames(engine, o
         engine.set_chunk_frames(0)
     assert np.array_equal(ta, tb) and sa.tobytes() == sb.tobytes()
     st_a.free(); st_b.free()
+
+
+@pytest.mark.gpu
+def test_submit_wait_equals_the_blocking_pipeline(engine, oracle):
+    """cvb_pipeline_submit / cvb_pipeline_wait: batches in flight back to back (formats and chunk layouts changing between
+    them, the change-detector state evolving from batch to batch) give what the blocking calls give."""
+    from chessboard_vision_b200.engine import (grid_rects, SQ_PD_STATS, SQ_PD_SET_REF, SQ_CD_CALIBRATE, SQ_CD_DETECT,
+                                               SQ_CD_UPDATE)
+    H, W, S, n = 270, 480, 160, 6
+    M = engine.get_perspective_transform(synth.calib_points(H, W), [[0, 0], [S, 0], [0, S], [S, S]])
+    rects, _ = grid_rects(S)
+    cal = engine.pipeline_params(squares=engine.square_params(ops=SQ_PD_STATS | SQ_PD_SET_REF | SQ_CD_CALIBRATE), board_size=S)
+    run = engine.pipeline_params(squares=engine.square_params(ops=SQ_PD_STATS | SQ_CD_DETECT | SQ_CD_UPDATE), board_size=S)
+    batches = []
+    for k, fmt in enumerate(["bgr", "yuy2", "bgr", "nv12", "nv12", "bgr"]):
+        f = np.stack([synth.board_frame(H, W, 10 * k + i) for i in range(n)])
+        if fmt != "bgr":
+            f = np.stack([synth.bgr_to_yuv(x, fmt) for x in f])
+        host = engine.pinned(f.shape)
+        host[...] = f
+        batches.append((host, fmt, cal if k == 0 else run))
+    st_a, st_b = engine.new_state(n, S, S), engine.new_state(n, S, S)
+    for chunk in (0, 4):
+        engine.set_chunk_frames(chunk)
+        try:
+            ref = [engine.pipeline(h, M, rects, p, st_a, fmt=fmt) for h, fmt, p in batches]
+            tickets = [engine.pipeline_submit(h, M, rects, p, st_b, fmt=fmt) for h, fmt, p in batches]   # all in flight
+            got = [engine.pipeline_wait(t) for t in tickets]
+        finally:
+            engine.set_chunk_frames(0)
+        for (ta, sa), (tb, sb) in zip(ref, got):
+            assert np.array_equal(ta, tb) and sa.tobytes() == sb.tobytes()
+        for plane in range(5):
+            assert np.array_equal(st_a.get(0, plane), st_b.get(0, plane))
+    with pytest.raises(ValueError):
+        engine.pipeline_submit(batches[0][0][:, ::2], M, rects, run, st_b)        # not contiguous: read after the call returns
+    st_a.free(); st_b.free()
+    for h, _, _ in batches:
+        engine.lib.cvb_host_free(h.ctypes.data)
