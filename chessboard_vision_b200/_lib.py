@@ -56,7 +56,7 @@ class PipelineParams(C.Structure):
                 ("warp_enhanced", C.c_int), ("board_size", C.c_int), ("rotate_180", C.c_int), ("reserved", C.c_int)]
 
 
-HOUGH_MAX_CIRCLES, HOUGH_MAX_DIM = 16, 128
+HOUGH_MAX_CIRCLES, HOUGH_MAX_DIM, HOUGH_MAX_DIM_GLOBAL = 16, 128, 254
 HOUGH_OK, HOUGH_SKIPPED = 0, 1
 
 

@@ -119,7 +119,7 @@ void cvb_destroy(cvb_handle *h)
     DevBuf *bufs[] = {&h->ws_lab, &h->ws_prof, &h->ws_in, &h->ws_sharp, &h->ws_enh, &h->ws_gray, &h->ws_blur, &h->ws_bin, &h->ws_warp,
                       &h->ws_plane, &h->ws_plane2, &h->ws_hist, &h->ws_lut, &h->ws_minmax, &h->ws_ohist, &h->ws_otsu,
                       &h->ws_stats, &h->ws_otsu_all, &h->ws_rects, &h->ws_select, &h->ws_mats, &h->ws_masks,
-                      &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res, &h->ws_stage, &h->ws_overlay};
+                      &h->ws_hough_sq, &h->ws_hough_sel, &h->ws_hough_res, &h->ws_hough_gws, &h->ws_stage, &h->ws_overlay};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : h->ev_ticket) if (e) cudaEventDestroy(e);
@@ -839,13 +839,16 @@ static int hough_impl(cvb_handle *h, const uint8_t *planes, int n, int PH, int P
                     "square %d (%d,%d %dx%d) outside the %dx%d plane", i, rects[i].x, rects[i].y, rects[i].w, rects[i].h, PW, PH);
         bool used = select == nullptr;
         for (int f = 0; f < n && !used; ++f) used = select[(size_t)f * n_sq + i] != 0;
-        // the size limit only concerns squares some frame selects (ADVICE r1: an unselected large rectangle is harmless)
-        CVB_REQUIRE(!used || (rects[i].w <= CVB_HOUGH_MAX_DIM && rects[i].h <= CVB_HOUGH_MAX_DIM),
+        // the size limit only concerns squares some frame selects (an unselected large rectangle is harmless)
+        CVB_REQUIRE(!used || (rects[i].w <= CVB_HOUGH_MAX_DIM_GLOBAL && rects[i].h <= CVB_HOUGH_MAX_DIM_GLOBAL),
                     "square %d is %dx%d: the Hough kernel handles squares up to %d pixels a side", i, rects[i].w, rects[i].h,
-                    CVB_HOUGH_MAX_DIM);
+                    CVB_HOUGH_MAX_DIM_GLOBAL);
     }
     std::vector<cvb_hough_square> sq(n_sq);
     CVB_TRY(cvb_hough_geometry(rects, n_sq, p, sq.data()));
+    for (int i = 0; i < n_sq; ++i)      // accumulator cells are addressed by 8-bit coordinates and 16-bit indices in the kernel
+        CVB_REQUIRE(sq[i].acc_rows <= 253 && sq[i].acc_cols <= 253,
+                    "square %d: a %dx%d accumulator (dp %.2f) exceeds 253 cells a side", i, sq[i].acc_cols, sq[i].acc_rows, (double)p->dp);
     WS(ws_hough_sq, cvb_hough_square, n_sq, d_sq);
     if (h->hough_cache.size() != sq.size() || memcmp(h->hough_cache.data(), sq.data(), sizeof(cvb_hough_square) * n_sq) != 0) {
         CVB_CHECK_CUDA(cudaMemcpyAsync(d_sq, sq.data(), sizeof(cvb_hough_square) * n_sq, cudaMemcpyHostToDevice, h->stream));

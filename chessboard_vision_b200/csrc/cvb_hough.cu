@@ -1,6 +1,7 @@
 // cv2.HoughCircles(gray, HOUGH_GRADIENT, ...) for a batch of small squares -- the step after the
 // per-square statistics in PieceDetector._detect_circle_unified (piece_detector.py:210-270),
-// SURVEY.md 8f rank 1.  One CTA owns one square; the whole transform lives in shared memory.
+// SURVEY.md 8f rank 1.  One CTA owns one square; the whole transform lives in shared memory (squares up to
+// CVB_HOUGH_MAX_DIM a side) or, for larger squares, in a global-memory slice of the same layout.
 //
 // OpenCV imgproc/src/hough.cpp (HoughCirclesGradient), restated (oracle: orc_hough_circles):
 //   A  Sobel 3x3 (replicate border), Canny(dx, dy, max(1, param1/2), param1) with L1 magnitude
@@ -51,13 +52,17 @@ CVB_DEV void sobel_at(const uint8_t *g, int gp, int y, int x, int &gx, int &gy)
     gy = (q + 2 * r + s) - (a + 2 * b + c);
 }
 
+// GWS: squares whose workspace does not fit shared memory (more than CVB_HOUGH_MAX_DIM pixels a side) run the very same
+// phases on a slice of global memory per CTA -- slower votes, identical circles.
+template <bool GWS>
 __global__ void __launch_bounds__(HNT, 4) k_hough(const uint8_t *__restrict__ planes, size_t plane_stride, int PW,
                                               const cvb_hough_square *__restrict__ squares, int n_sq,
                                               const uint8_t *__restrict__ select, float dp, float idp, int canny_low,
                                               int canny_high, int acc_thr, HoughLayout L,
-                                              cvb_hough_result *__restrict__ out)
+                                              cvb_hough_result *__restrict__ out, uint8_t *gws)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint8_t *smem = GWS ? gws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)L.total : smem_dyn;
     __shared__ HoughMisc M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sq = blockIdx.x, frame = blockIdx.y;
@@ -393,17 +398,32 @@ int launch_hough(cvb_handle *h, const uint8_t *planes, int n, size_t plane_strid
     const size_t uni_b = std::max(late_b, early_b + 4 * 512);
     L.dir_cap = (int)((uni_b - early_b) / 4);
     L.total = L.off_union + (int)up16(uni_b);
-    CVB_REQUIRE(L.total <= 220 * 1024, "Hough workspace of %d bytes per square exceeds shared memory", L.total);
-    const void *fn = (const void *)k_hough;
-    auto it = h->squares_smem_attr.find(fn);
-    if (it == h->squares_smem_attr.end() || it->second < (size_t)L.total) {
-        CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        h->squares_smem_attr[fn] = (size_t)L.total;
+    if (L.total <= 220 * 1024) {
+        const void *fn = (const void *)k_hough<false>;
+        auto it = h->squares_smem_attr.find(fn);
+        if (it == h->squares_smem_attr.end() || it->second < (size_t)L.total) {
+            CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            h->squares_smem_attr[fn] = (size_t)L.total;
+        }
+        PROF(h, "k_hough");
+        k_hough<false><<<dim3(n_sq, n), HNT, L.total, h->stream>>>(planes, plane_stride, PW, d_squares, n_sq, d_select, dp, idp,
+                                                                   canny_low, canny_high, acc_thr, L, out, nullptr);
+        LAUNCH_CHECK(h);
+        return CVB_OK;
     }
-    PROF(h, "k_hough");
-    k_hough<<<dim3(n_sq, n), HNT, L.total, h->stream>>>(planes, plane_stride, PW, d_squares, n_sq, d_select, dp, idp, canny_low,
-                                                        canny_high, acc_thr, L, out);
-    LAUNCH_CHECK(h);
+    // larger squares: the same kernel on a global-memory slice per CTA, as many frames per launch as 2 GB of slices hold
+    const size_t per_frame = (size_t)L.total * n_sq;
+    const int fpl = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)2 << 30) / per_frame));
+    uint8_t *gws = nullptr;
+    CVB_TRY(cvb_ws(h, h->ws_hough_gws, per_frame * fpl, (void **)&gws));
+    for (int f0 = 0; f0 < n; f0 += fpl) {
+        const int cnt = std::min(fpl, n - f0);
+        PROF(h, "k_hough_gws");
+        k_hough<true><<<dim3(n_sq, cnt), HNT, 0, h->stream>>>(planes + (size_t)f0 * plane_stride, plane_stride, PW, d_squares, n_sq,
+                                                              d_select ? d_select + (size_t)f0 * n_sq : nullptr, dp, idp, canny_low,
+                                                              canny_high, acc_thr, L, out + (size_t)f0 * n_sq, gws);
+        LAUNCH_CHECK(h);
+    }
     return CVB_OK;
 }
 

@@ -98,7 +98,7 @@ struct cvb_handle {
     DevBuf ws_masks;
     // Hough: staged per-square geometry (content-compared), select bytes, results
     std::vector<cvb_hough_square> hough_cache;
-    DevBuf ws_hough_sq, ws_hough_sel, ws_hough_res;
+    DevBuf ws_hough_sq, ws_hough_sel, ws_hough_res, ws_hough_gws;
     DevBuf ws_stage;            // the two chunk staging buffers of the host-buffer pipeline (its own: see pipeline_fmt_impl)
     DevBuf ws_overlay;          // display list + circle span tables + stamp masks of the last cvb_overlay_dev call
     void *pinned = nullptr;

@@ -270,11 +270,14 @@ int cvb_state_reset(cvb_handle *h, cvb_state *s, int stream);
 /* ---- PieceDetector._detect_circle_unified: cv2.HoughCircles per square ------------- */
 /* cv2.HoughCircles(gray, HOUGH_GRADIENT, dp, minDist, param1, param2, minRadius,
  * maxRadius) on every selected square of n gray planes  piece_detector.py:210-270.
- * One CTA per square, the whole transform in shared memory; squares up to
- * CVB_HOUGH_MAX_DIM pixels a side.  Bit-identical to OpenCV 4.13 (circle list,
- * order, f32 values).                                                            */
+ * One CTA per square, the whole transform in shared memory for squares up to
+ * CVB_HOUGH_MAX_DIM pixels a side; larger squares, up to CVB_HOUGH_MAX_DIM_GLOBAL (and
+ * at most 253 accumulator cells a side, i.e. dp >= 1.01 at 254 pixels), run the same kernel
+ * on a global-memory workspace.  Bit-identical to OpenCV 4.13 (circle list, order, f32
+ * values).                                                                       */
 #define CVB_HOUGH_MAX_CIRCLES 16   /* circles stored per square (minDist = side/3 allows <= 16) */
 #define CVB_HOUGH_MAX_DIM     128
+#define CVB_HOUGH_MAX_DIM_GLOBAL 254   /* (side + 2)^2 padded pixels are indexed with 16 bits */
 enum { CVB_HOUGH_OK = 0, CVB_HOUGH_SKIPPED = 1 };
 typedef struct {
     float  dp;                  /* 1.2 (values < 1 are raised to 1, as OpenCV does)   piece_detector.py:235 */

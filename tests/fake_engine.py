@@ -177,8 +177,8 @@ class FakeEngine:
         out = np.zeros((pl.shape[0], len(rects)), HOUGH_DTYPE)
         for f in range(pl.shape[0]):
             for i, (x, y, w, h) in enumerate(rects):
-                if w > _lib.HOUGH_MAX_DIM or h > _lib.HOUGH_MAX_DIM:
-                    raise ValueError("square larger than %d" % _lib.HOUGH_MAX_DIM)
+                if w > _lib.HOUGH_MAX_DIM_GLOBAL or h > _lib.HOUGH_MAX_DIM_GLOBAL:
+                    raise ValueError("square larger than %d" % _lib.HOUGH_MAX_DIM_GLOBAL)
                 if sel is not None and not sel[f, i]:
                     out[f, i]["status"] = _lib.HOUGH_SKIPPED
                     continue

@@ -47,3 +47,34 @@ def board_image(size, seed=0):
 
 def digest(img):
     return hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest()
+
+
+def random_display_list(rng, H, W, n_ops):
+    """every op kind, opaque and blended, grouped shapes, text stamps, partly or wholly outside the image"""
+    from chessboard_vision_b200.overlay import DisplayList
+    import cv2
+    dl = DisplayList()
+    weights = ((1.0, 0.0), (0.3, 0.7), (0.5, 0.5), (0.4, 0.6), (0.6, 0.4), (0.9, 0.35), (0.0, 1.0))
+    while len(dl.ops) < n_ops:
+        kind = int(rng.integers(0, 5))
+        color = tuple(int(c) for c in rng.integers(0, 256, 3))
+        a, b = weights[int(rng.integers(0, len(weights)))]
+        x, y = int(rng.integers(-30, W + 30)), int(rng.integers(-30, H + 30))
+        if kind == 0:
+            dl.rectangle((x, y), (x + int(rng.integers(-40, 90)), y + int(rng.integers(-40, 90))), color, a, b)
+        elif kind == 1:
+            dl.circle((x, y), int(rng.integers(0, 60)), color, a, b)
+        elif kind == 2:
+            dl.put_text("".join(chr(int(c)) for c in rng.integers(33, 127, int(rng.integers(1, 9)))), (x, y),
+                        cv2.FONT_HERSHEY_SIMPLEX, float(rng.uniform(0.4, 1.6)), color, int(rng.integers(1, 5)))
+        elif kind == 3:                                          # shapes on one overlay copy
+            g = dl.group()
+            for _ in range(int(rng.integers(2, 5))):
+                if rng.integers(0, 2):
+                    dl.rectangle((x, y), (x + int(rng.integers(0, 70)), y + int(rng.integers(0, 70))), color, a, b, g)
+                else:
+                    dl.circle((x, y), int(rng.integers(0, 40)), color, a, b, g)
+                x, y = x + int(rng.integers(-30, 31)), y + int(rng.integers(-30, 31))
+        else:
+            dl.line((x, 0), (x, H), color) if rng.integers(0, 2) else dl.line((0, y), (W, y), color)
+    return dl

@@ -133,10 +133,36 @@ def test_hough_golden_cv2(engine):
             assert np.array_equal(rec["xyr"][:k].view(np.uint32), want[:k].view(np.uint32)), (ci, i)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_hough_large_squares_global_workspace(engine, oracle, seed):
+    """Squares of 129..254 pixels a side (a 4K camera's 1600-pixel board gives 200-pixel squares) do not fit shared
+    memory: the same kernel on a global-memory workspace, same circles as the oracle; mixed with small squares and
+    several frames per call."""
+    plane, rects = synth.shape_atlas(50 + seed, 7, 129, 254, 1024)
+    small_plane, small = synth.shape_atlas(60 + seed, 3, 20, 100, 1024)
+    H = max(plane.shape[0], small_plane.shape[0])
+    both = np.zeros((H + small_plane.shape[0], 1024), np.uint8)
+    both[:plane.shape[0]] = plane
+    both[H:H + small_plane.shape[0]] = small_plane
+    rects = rects + [(x, y + H, w, h) for (x, y, w, h) in small]
+    total = 0
+    for c in (dict(dp=1.2, param1=100, param2=25), dict(dp=1.05, param1=60, param2=12, min_radius=5, max_radius=90, min_dist=9.0),
+              dict(dp=2.0, param1=40, param2=8, min_radius_ratio=0.1, max_radius_ratio=0.5)):
+        total += _check(engine, oracle, both, rects, engine.hough_params(**c), max(1.0, c["dp"]))
+    assert total > 5
+    frames = np.stack([both, both[::-1].copy()])                 # two frames in one call
+    got = engine.hough(frames, rects)
+    one = engine.hough(both[::-1].copy(), rects)
+    assert got[1].tobytes() == one[0].tobytes()
+
+
 def test_hough_rejects_oversized_squares_and_bad_parameters(engine):
-    plane = np.zeros((200, 200), np.uint8)
+    plane = np.zeros((300, 300), np.uint8)
     with pytest.raises(ValueError):
-        engine.hough(plane, [(0, 0, 129, 64)])
+        engine.hough(plane, [(0, 0, 255, 64)])
+    with pytest.raises(ValueError):
+        engine.hough(plane, [(0, 0, 254, 254)], engine.hough_params(dp=1.0))     # 254 + 2 accumulator cells a side
+    plane = np.zeros((200, 200), np.uint8)
     with pytest.raises(ValueError):
         engine.hough(plane, [(150, 150, 64, 64)])
     with pytest.raises(ValueError):

@@ -30,35 +30,6 @@ def test_draw_interface_is_the_reference_picture(engine, name, size, state):
     assert np.array_equal(vis, ref)
 
 
-def _random_list(rng, H, W, n_ops):
-    import cv2
-    dl = DisplayList()
-    weights = ((1.0, 0.0), (0.3, 0.7), (0.5, 0.5), (0.4, 0.6), (0.6, 0.4), (0.9, 0.35), (0.0, 1.0))
-    while len(dl.ops) < n_ops:
-        kind = int(rng.integers(0, 5))
-        color = tuple(int(c) for c in rng.integers(0, 256, 3))
-        a, b = weights[int(rng.integers(0, len(weights)))]
-        x, y = int(rng.integers(-30, W + 30)), int(rng.integers(-30, H + 30))
-        if kind == 0:
-            dl.rectangle((x, y), (x + int(rng.integers(-40, 90)), y + int(rng.integers(-40, 90))), color, a, b)
-        elif kind == 1:
-            dl.circle((x, y), int(rng.integers(0, 60)), color, a, b)
-        elif kind == 2:
-            dl.put_text("".join(chr(int(c)) for c in rng.integers(33, 127, int(rng.integers(1, 9)))), (x, y),
-                        cv2.FONT_HERSHEY_SIMPLEX, float(rng.uniform(0.4, 1.6)), color, int(rng.integers(1, 5)))
-        elif kind == 3:                                          # shapes on one overlay copy
-            g = dl.group()
-            for _ in range(int(rng.integers(2, 5))):
-                if rng.integers(0, 2):
-                    dl.rectangle((x, y), (x + int(rng.integers(0, 70)), y + int(rng.integers(0, 70))), color, a, b, g)
-                else:
-                    dl.circle((x, y), int(rng.integers(0, 40)), color, a, b, g)
-                x, y = x + int(rng.integers(-30, 31)), y + int(rng.integers(-30, 31))
-        else:
-            dl.line((x, 0), (x, H), color) if rng.integers(0, 2) else dl.line((0, y), (W, y), color)
-    return dl
-
-
 @pytest.mark.parametrize("seed,shape,n_ops", [(0, (97, 131), 40), (1, (480, 640), 200), (2, (33, 35), 64), (3, (800, 800), 1500),
                                               (4, (1, 1), 10), (5, (8, 2048), 120)])
 def test_random_display_lists_against_the_interpreter(engine, seed, shape, n_ops):
@@ -66,7 +37,7 @@ def test_random_display_lists_against_the_interpreter(engine, seed, shape, n_ops
     rng = np.random.default_rng(seed)
     H, W = shape
     img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
-    dl = _random_list(rng, H, W, n_ops)
+    dl = oc.random_display_list(rng, H, W, n_ops)
     ops, n, masks = dl.pack()
     assert n >= n_ops
     got = engine.overlay(img, ops, n, masks)
@@ -77,7 +48,7 @@ def test_batch_and_device_resident(engine):
     from oracle import overlay as ov
     rng = np.random.default_rng(9)
     imgs = rng.integers(0, 256, (3, 120, 200, 3), dtype=np.uint8)
-    dl = _random_list(rng, 120, 200, 50)
+    dl = oc.random_display_list(rng, 120, 200, 50)
     ops, n, masks = dl.pack()
     got = engine.overlay(imgs, ops, n, masks)
     for i in range(3):

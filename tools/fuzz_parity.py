@@ -1,12 +1,16 @@
 """Randomised parity sweep on the GPU: random frame sizes and contents through the enhancer chain, the analysis tail,
-the warp and the square statistics, each compared bit for bit with the CPU oracle (test infrastructure).
+the warp, the square statistics, the YUV ingest and random overlay display lists, each compared bit for bit with the CPU
+oracle (test infrastructure).
 usage: python tools/fuzz_parity.py [cases] [seed]      (tests/test_gpu_e2e_parity.py runs `sweep` under pytest)"""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import oracle as O
+import overlay_common
+from oracle import overlay as OV
 from chessboard_vision_b200 import synth
 from chessboard_vision_b200.engine import grid_rects, SQ_PD_STATS, SQ_CD_CALIBRATE, SQ_CD_DETECT, SQ_CD_UPDATE
 
@@ -63,6 +67,13 @@ def sweep(eng, cases=40, seed=0, verbose=True):
                 ok &= int(s["sum"]) == o["sum"] and int(s["sumsq"]) == o["sumsq"] and int(s["cd_changed"]) == cnt
                 ok &= (np.float32(s["cd_zmax"]) == np.float32(zmax)) or (np.isnan(s["cd_zmax"]) and np.isnan(zmax))
             st.free()
+        if H % 2 == 0 and W % 2 == 0:      # camera formats: device conversion against the integer BT.601 of cv2.cvtColor
+            for fmt in ("yuy2", "nv12"):
+                raw = synth.bgr_to_yuv(f, fmt)
+                ok &= np.array_equal(eng.cvt_to_bgr(raw, fmt), O.yuv_to_bgr(raw, fmt))
+        dl = overlay_common.random_display_list(rng, S, S, int(rng.integers(1, 60)))
+        ops, n_ops, masks = dl.pack()
+        ok &= np.array_equal(eng.overlay(w, ops, n_ops, masks), OV.apply_display_list(w, ops, n_ops, masks))
         if not ok:
             bad += 1
             print("MISMATCH case", c, (H, W), kind, "S", S, "flip", flip)
