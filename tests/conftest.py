@@ -24,4 +24,11 @@ def engine():
     from chessboard_vision_b200.engine import Engine
     e = Engine(0)
     yield e
+    # with the debug build (CVB200_LIB=.../libcvb200_dbg.so) the whole session doubles as an index-check run
+    import ctypes
+    line = ctypes.c_int(0)
+    bad = e.lib.cvb_debug_bounds_violations(e.h, ctypes.byref(line))
     e.close()
+    if bad >= 0:
+        print("\n[debug build] index checks that failed during the session: %d (first at source line %d)" % (bad, line.value))
+    assert bad <= 0, "index check failed %d time(s), first at source line %d" % (bad, line.value)
