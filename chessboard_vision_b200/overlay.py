@@ -153,6 +153,22 @@ class BoardOverlay:
         dl.put_text("FPS: %.1f" % fps, (S - 150, 30), font, 0.6, (0, 255, 255), 2)  # :385-386
         return dl
 
+    @staticmethod
+    def session_state(session, noise_active):
+        """The arguments of display_list read off a GameSession exactly where _draw_interface reads them
+        (game_session.py:297-386): grid lines, last move, lifted square, radar destinations, pieces, side to move, fps.
+        `session.game.board` is a python-chess Board (or None)."""
+        board = session.game.board
+        fr = lambda sq: (sq & 7, sq >> 3)                 # chess.square_file / chess.square_rank
+        last = None
+        if board and len(board.move_stack) > 0:
+            mv = board.peek()
+            last = (fr(mv.from_square), fr(mv.to_square))
+        return dict(noise_active=bool(noise_active), grid_lines_x=session.grid.grid_lines_x, grid_lines_y=session.grid.grid_lines_y,
+                    last_move=last, lifted=session.lifted_piece_square, radar=list(session.current_radar_destinations),
+                    pieces=(None if not board else {fr(sq): p.symbol() for sq, p in board.piece_map().items()}),
+                    white_to_move=bool(board and board.turn), fps=session.fps_display)
+
     def draw(self, vis, dl):
         """Apply a DisplayList.  A NumPy image is drawn in place (as cv2 does) and returned; a DevArray stays on the device."""
         ops, n, masks = dl.pack()

@@ -34,6 +34,10 @@ class FakeEngine:
     h = 1
     launches = 0
 
+    def overlay(self, img, ops, n_ops, masks=b""):
+        from oracle import overlay as OV
+        return OV.apply_display_list(img, ops, n_ops, masks)
+
     def enhance_params(self, clip=3.0, tiles=(8, 8), d=9, sigma_color=75.0, sigma_space=75.0, profile=None):
         return dict(clip=clip, tiles=tiles, profile=profile)
 

@@ -93,6 +93,9 @@ class Board:
     def piece_at(self, sq):
         return self._p.get(sq)
 
+    def piece_map(self):
+        return dict(self._p)
+
     @property
     def legal_moves(self):
         return _LegalMoves(self)

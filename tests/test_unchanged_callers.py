@@ -80,3 +80,45 @@ def test_replay_matches_the_callers(fake, monkeypatch):
     finally:
         for name in ch.VISION:
             sys.modules.pop(name, None)
+
+
+def test_patched_draw_interface_in_a_live_session(fake):
+    """INTEGRATION.md "Board overlay": GameSession._draw_interface replaced by BoardOverlay.session_state +
+    draw_interface.  Inside the reference's own GameSession, on every frame of a game (grid from the calibration file,
+    noise states, the e2e4 highlight, FPS text), the display list -- interpreted with OpenCV's arithmetic, no GPU here --
+    is the picture the original method hands to cv2.imshow."""
+    import numpy as np
+    import cv2
+    from chessboard_vision_b200.overlay import BoardOverlay
+    frames = ch.scenario_game()
+    with ch.caller_env("reference") as st:
+        import game_session
+        game_session.time = ch.FakeClock()
+        original = game_session.GameSession._draw_interface
+        shown, compared = [], []
+        cv2.imshow = lambda name, img: shown.append((name, img.copy()))
+        overlay = BoardOverlay(fake)
+
+        def patched(self, vis, board_size, noise_state, img_raw):
+            before = vis.copy()
+            shown.clear()
+            original(self, vis, board_size, noise_state, img_raw)
+            want = [img for name, img in shown if name == "Tabuleiro"][0]
+            with self.board_lock:
+                state = BoardOverlay.session_state(self, noise_state == game_session.NoiseState.NOISE_ACTIVE)
+            got = overlay.draw_interface(before, board_size, **state)
+            compared.append((bool(np.array_equal(got, want)), bool(state["last_move"]), state["noise_active"]))
+        game_session.GameSession._draw_interface = patched
+        try:
+            s = game_session.GameSession()
+            cap = ch.FakeCap(frames)
+            assert s.on_calibration_requested(cap)
+            while True:
+                ok, img = cap.read()
+                if not ok:
+                    break
+                s.on_frame(img)
+        finally:
+            game_session.GameSession._draw_interface = original
+    assert len(compared) >= 10 and all(c[0] for c in compared)
+    assert any(c[1] for c in compared)                      # frames after the move carry the last-move highlight
