@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import overlay_common as oc
 from chessboard_vision_b200._lib import OverlayOp
-from chessboard_vision_b200.overlay import BoardOverlay, DisplayList
+from chessboard_vision_b200.overlay import BoardOverlay
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(HERE, "golden", "overlay.json")))

@@ -37,9 +37,6 @@ def reference_draw(gs_mod, chess, size, state, shown):
         lm = state.get("last_move")
         board.move_stack = [1] if lm else []
         board.peek = lambda: chess.Move(chess.square(*lm[0]), chess.square(*lm[1]))
-
-        class _B:            # `if self.game.board` must be truthy for a board object
-            pass
     fake = types.SimpleNamespace(
         grid=types.SimpleNamespace(grid_lines_x=state.get("grid_lines_x"), grid_lines_y=state.get("grid_lines_y")),
         board_lock=threading.RLock(), game=types.SimpleNamespace(board=board),
