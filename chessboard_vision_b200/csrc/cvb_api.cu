@@ -1052,8 +1052,10 @@ static int pipeline_fmt_impl(cvb_handle *h, const uint8_t *frames, int format, i
     // (25 frames at 1080p: 6800 CTAs = 22.97 waves; 8 frames = 7.35 waves lose 8 %).
     int chunk = h->chunk_frames;
     if (chunk <= 0) {
-        chunk = 8;
-        if (format != CVB_FMT_BGR) {
+        // BGR: the copy is the bound, the first chunk's copy the only one nothing hides: about 50 MB per chunk (8 frames
+        // of 1080p, 2 of 3840 x 2160: a batch of eight 4K streams in ONE chunk would not overlap copy and kernels at all)
+        chunk = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)50 << 20) / fin));
+        if (format != CVB_FMT_BGR && fin * 12 <= ((size_t)100 << 20)) {
             const long tiles = (long)((W + 119) / 120) * ((H + 63) / 64), slots = 2L * h->sm_count;
             double best = 0;
             for (int c = 12; c <= 32; ++c) {
