@@ -872,6 +872,7 @@ int launch_fused_tma(cvb_handle *h, const uint8_t *lab, int n, int H, int W, con
     case 1: return launch_variant<1, 1024, 64, false, 2>(h, lab, a);   // one group of 1024, folded table, packed accumulation
     case 2: return launch_variant<1, 512, 64, true, 2>(h, lab, a);     // one group of 512, private table, packed
     case 3: return launch_variant<2, 512, 30, true, 0>(h, lab, a);     // two groups of 512 on 120 x 30 tiles, private table, scalar
+    case 4: return launch_variant<1, 512, 64, true, 0>(h, lab, a);     // one group of 512, private table, scalar
     default: return launch_pc<46, 256, 768, true, 0>(h, lab, a);       // producer / consumer warps, 120 x 46 tiles, private table
     }
 }
