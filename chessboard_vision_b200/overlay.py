@@ -75,6 +75,8 @@ class DisplayList:
                     g = (int(xs.min()) - pad, int(ys.min()) - (pad + h), box.shape[1], box.shape[0], rows.tobytes())
                     break
                 pad *= 2        # ink reached the canvas border: the text box under-estimated it
+            if len(cls._glyphs) >= 1024:      # an FPS read-out makes new strings for hours: keep the cache bounded
+                cls._glyphs.clear()
             cls._glyphs[key] = g
         return g
 
