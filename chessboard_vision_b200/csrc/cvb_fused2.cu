@@ -821,7 +821,6 @@ template <int TH, int NP, int NQ, bool LUTP, int ACC>
 int launch_pc(cvb_handle *h, const uint8_t *lab, Fused2Args &a)
 {
     using S = SmemPC<TH, LUTP>;
-    static_assert(((TH + 2 * BY) / 2) * RUNS <= NQ, "one bilateral item per consumer thread");
     auto kern = k_fused_pc<TH, NP, NQ, LUTP, ACC>;
     if (!h->fused_attr_done.count((const void *)kern)) {
         CVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
@@ -873,6 +872,7 @@ int launch_fused_tma(cvb_handle *h, const uint8_t *lab, int n, int H, int W, con
     case 2: return launch_variant<1, 512, 64, true, 2>(h, lab, a);     // one group of 512, private table, packed
     case 3: return launch_variant<2, 512, 30, true, 0>(h, lab, a);     // two groups of 512 on 120 x 30 tiles, private table, scalar
     case 4: return launch_variant<1, 512, 64, true, 0>(h, lab, a);     // one group of 512, private table, scalar
+    case 5: return launch_pc<64, 256, 512, false, 2>(h, lab, a);       // producer / consumer, 8 + 16 warps of 80 registers, 120 x 64 tiles, product table, packed
     default: return launch_pc<46, 256, 768, true, 0>(h, lab, a);       // producer / consumer warps, 120 x 46 tiles, private table
     }
 }

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DBG = os.path.join(ROOT, "chessboard_vision_b200", "libcvb200_dbg.so")
 
 
-@pytest.mark.parametrize("fused", ["", "0", "2", "3", "4"])
+@pytest.mark.parametrize("fused", ["", "0", "2", "3", "4", "5"])
 def test_no_index_violations(fused):
     if not os.path.exists(DBG):
         pytest.skip("libcvb200_dbg.so not built (python -c 'import __graft_entry__ as g; g.build()')")
