@@ -105,8 +105,8 @@ CVB_DEV void bilateral_item_abl(const uint32_t *sA, uint32_t *sB, const float *s
 
 }
 
-template <int NT, bool LUTP, int ACC>
-__global__ void __launch_bounds__(NT, 1) k_bil_only(const uint32_t *tile, const float *wlut, const __grid_constant__ Fused2Args a,
+template <int NT, bool LUTP, int ACC, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_bil_only(const uint32_t *tile, const float *wlut, const __grid_constant__ Fused2Args a,
                                                    int reps, uint32_t *out, long long *cyc)
 {
     constexpr int TH = 64, BH = TH + 2, AH = BH + 8;
@@ -134,22 +134,23 @@ __global__ void __launch_bounds__(NT, 1) k_bil_only(const uint32_t *tile, const 
     out[blockIdx.x * NT + tid] = sB[tid];
 }
 
-template <int NT, bool LUTP, int ACC>
+template <int NT, bool LUTP, int ACC, int MINB = 1>
 void run(const char *name, const uint32_t *d_tile, const float *d_w, const Fused2Args &a)
 {
     constexpr int TH = 64, BH = TH + 2, AH = BH + 8;
     const size_t smem = (size_t)AW * AH * 4 + (size_t)BW * BH * 4 + (LUTP ? 768 * 32 * 4 : 10 * 768 * 4);
-    auto k = k_bil_only<NT, LUTP, ACC>;
+    auto k = k_bil_only<NT, LUTP, ACC, MINB>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     uint32_t *out; long long *cyc;
-    cudaMalloc(&out, 148 * NT * 4); cudaMalloc(&cyc, 148 * 8);
+    constexpr int NCTA = 148 * MINB;                             // MINB CTAs resident per SM, each on its own tile
+    cudaMalloc(&out, NCTA * NT * 4); cudaMalloc(&cyc, NCTA * 8);
     const int reps = 40;
-    k<<<148, NT, smem>>>(d_tile, d_w, a, 2, out, cyc);
-    k<<<148, NT, smem>>>(d_tile, d_w, a, reps, out, cyc);
+    k<<<NCTA, NT, smem>>>(d_tile, d_w, a, 2, out, cyc);
+    k<<<NCTA, NT, smem>>>(d_tile, d_w, a, reps, out, cyc);
     cudaError_t e = cudaDeviceSynchronize();
-    long long c[148]; cudaMemcpy(c, cyc, sizeof c, cudaMemcpyDeviceToHost);
-    double avg = 0; for (int i = 0; i < 148; ++i) avg += c[i]; avg /= 148;
-    const double px = (double)BW * BH * reps;                    // bilateral outputs per CTA
+    long long c[NCTA]; cudaMemcpy(c, cyc, sizeof c, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < NCTA; ++i) avg += c[i]; avg /= NCTA;
+    const double px = (double)BW * BH * reps * MINB;             // bilateral outputs per SM in that time
     const double clk_per_px_sm = avg / px;                        // SM clocks per output pixel
     // a 1080p frame: 272 tiles of 124 x 66 bilateral outputs over 148 SMs at 1.965 GHz
     printf("%-52s %s  %.3f SM-clk per pixel = %.1f clk per warp-pixel-group and SMSP -> %.1f us per 1080p frame\n", name,
@@ -195,6 +196,13 @@ int main()
     run<1024, true, 2>("private table, packed accumulation, 1024 threads", d_tile, d_w, a);
     run<1024, false, 2>("folded table,  packed accumulation, 1024 threads", d_tile, d_w, a);
     // ablations of the scalar private-table form (not the filter any more: which part costs what)
+    // two CTAs per SM, as the shipped kernel runs (product table: two private tables do not fit)
+    run<512, false, 0, 2>("2 CTAs x 512, product table, scalar (the shipped form)", d_tile, d_w, a);
+    run<512, false, 2, 2>("2 CTAs x 512, product table, packed (64 registers)", d_tile, d_w, a);
+    run<384, false, 2, 2>("2 CTAs x 384, product table, packed (85 registers)", d_tile, d_w, a);
+    run<352, false, 2, 2>("2 CTAs x 352, product table, packed (93 registers)", d_tile, d_w, a);
+    run<256, false, 2, 2>("2 CTAs x 256, product table, packed (128 registers)", d_tile, d_w, a);
+    run<352, false, 0, 2>("2 CTAs x 352, product table, scalar", d_tile, d_w, a);
     run<1024, true, 10>("ablation: nothing removed", d_tile, d_w, a);
     run<1024, true, 11>("ablation: constant weights (no VABSDIFF4 / LEA / LDS / FMUL)", d_tile, d_w, a);
     run<1024, true, 14>("ablation: distance but no table lookup (no LEA / LDS / FMUL)", d_tile, d_w, a);
